@@ -1,0 +1,261 @@
+/*
+ * rt_b200.h -- C ABI of the B200-native renderer core (librt_b200.so).
+ *
+ * This is the drop-in boundary for the render hot path of ACEfanatic02/par_raytracer.
+ * The reference has no plugin / FFI layer; the seam is the set of static C++ functions
+ *
+ *     Render(Camera*, Scene*, u32 w, u32 h) -> Framebuffer      main.cpp:301-358
+ *     RenderTask(RenderJob*, DebugCounters*)                    main.cpp:267-283
+ *     RenderPixel(RenderJob*, DebugCounters*, x, y) -> Vector4  main.cpp:224-265
+ *     TraceRayColor(Ray, Scene*, iters, dbg, rng) -> Vector4    raytracer.cpp:413-577
+ *     TraceRay(Ray, Scene*, RaycastHit*, dbg) -> bool           raytracer.cpp:159-232
+ *
+ * Each entry point below names the reference function it replaces. Plain pointers and
+ * sizes only; no C++ / torch types. All structs are POD with the field order of the
+ * reference struct they mirror so the host shim is a field copy.
+ *
+ * There is NO CPU fallback behind this interface: every compute entry point runs CUDA
+ * kernels on the device the scene was created on and fails with RT_ERR_CUDA otherwise.
+ */
+#ifndef RT_B200_H_
+#define RT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_ABI_VERSION 1
+
+/* status codes (reference has no error convention: brt.h:38-41 asserts print and continue) */
+#define RT_OK          0
+#define RT_ERR_ARG    -1
+#define RT_ERR_CUDA   -2
+#define RT_ERR_NOMEM  -3
+#define RT_ERR_STATE  -4
+
+/* ---- geometry.h:4-12 ------------------------------------------------------------ */
+typedef struct rt_ray {
+    float origin[3];
+    float direction[3];
+} rt_ray;                                   /* == Ray, 24 B */
+
+/* ---- main.cpp:133-143 ----------------------------------------------------------- */
+typedef struct rt_camera {
+    float tan_a2;
+    float aspect;
+    float inv_width;
+    float inv_height;
+    float position[3];
+    float forward[3];
+    float right[3];
+    float up[3];
+} rt_camera;                                /* == Camera, 64 B */
+
+/* ---- bsphere.cpp:316-320 -------------------------------------------------------- */
+typedef struct rt_bsphere {
+    float center[3];
+    float radius;
+    uint32_t c0;                            /* 0 == leaf sentinel (index 0 is the root) */
+    uint32_t c1;
+} rt_bsphere;                               /* == BoundingSphere, 24 B */
+
+/* ---- scene.h:3-15 --------------------------------------------------------------- */
+#define RT_LIGHT_DIRECTIONAL 0
+#define RT_LIGHT_POINT       1
+typedef struct rt_light {
+    int32_t type;
+    float color[4];
+    float position[3];
+    float facing[3];
+    float falloff;
+} rt_light;                                 /* == LightSource, 48 B */
+
+/* ---- mesh.h:8-13 ---------------------------------------------------------------- */
+typedef struct rt_texture {
+    uint32_t size_x;
+    uint32_t size_y;
+    uint32_t channels;                      /* 1..4, u8 per channel, row-major, as stbi_load returns */
+    const uint8_t *texels;
+} rt_texture;                               /* == Texture, 24 B */
+
+/* ---- mesh.h:15-32 (texture pointers become indices into rt_scene_desc.textures) - */
+typedef struct rt_material {
+    float specular_intensity;
+    float index_of_refraction;
+    float alpha;
+    float ambient_color[4];
+    float diffuse_color[4];
+    float specular_color[4];
+    float emissive_color[4];                /* carried, unused by the reference's integrator */
+    int32_t ambient_texture;                /* -1 == NULL */
+    int32_t diffuse_texture;
+    int32_t specular_texture;
+    int32_t alpha_texture;
+    int32_t bump_texture;                   /* already converted to a 3-channel normal map (texture.cpp:102-144) */
+} rt_material;
+
+/* ---- globals.h:3-7 -------------------------------------------------------------- */
+typedef struct rt_counters {
+    uint64_t ray_count;                     /* every TraceRay call: primary + shadow + bounce + alpha continuation */
+    uint64_t sphere_check_count;            /* bounding-sphere tests in OUR cluster hierarchy (differs from the reference's) */
+    uint64_t mesh_check_count;              /* leaf (triangle-cluster) scans in OUR hierarchy */
+} rt_counters;                              /* == DebugCounters */
+
+/* device-side measurements of the last call on a scene */
+typedef struct rt_stats {
+    double   gpu_ms;                        /* CUDA-event time of the render region on the scene's stream */
+    double   trace_ms;                      /* CUDA-event time summed over the trace kernels only (0 unless RT_FLAG_TIME_KERNELS) */
+    uint64_t kernel_launches;               /* kernels launched by the call */
+    uint64_t waves;                         /* wavefront iterations */
+    uint64_t closest_rays;                  /* rays through the closest-hit kernel */
+    uint64_t shadow_rays;                   /* rays through the occlusion kernel */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} rt_stats;
+
+/* ---- globals.h:9-22 (the members the hot path reads) + main.cpp:308-309 ----------
+ * base_seed: the per-(pixel,sample) seeding contract. Sample s of
+ * linear pixel index p draws from a RandomState seeded with
+ *     Random_Seed(base_seed ^ (p * 0x9E3779B97F4A7C15 + s))          (u64 wrap-around)
+ * random.h arithmetic unchanged. The oracle harness uses the same contract. */
+typedef struct rt_params {
+    float    ray_bias;
+    uint32_t reflection_samples;
+    uint32_t spec_samples;
+    uint32_t bounce_depth;
+    float    background_color[4];
+    uint32_t min_samples;                   /* main.cpp:308; fixed spp when min == max */
+    uint32_t max_samples;                   /* main.cpp:309 */
+    uint64_t base_seed;
+} rt_params;
+
+/* ---- raytracer.cpp:20-30 ------------------------------------------------------- */
+typedef struct rt_hit {
+    float    t;                             /* FLT_MAX on miss, as best_hit = { FLT_MAX } (raytracer.cpp:166) */
+    float    bw[3];
+    uint32_t vertex0;                       /* index into the group's index buffer, multiple of 3 */
+    float    position[3];
+    float    normal[3];                     /* geometric, normalised */
+    int32_t  object;                        /* index of the leaf BoundingSphere / SceneObject; -1 on miss (object == NULL) */
+    uint32_t hit;                           /* TraceRay's bool return */
+} rt_hit;
+
+/* ---- mesh.h:36-55, scene.h:22-36, bsphere.cpp:322-326 flattened to POD ---------- */
+typedef struct rt_scene_desc {
+    /* Mesh vertex streams (Mesh::positions / texcoords / normals / tangents) */
+    uint32_t n_positions;  const float *positions;   /* xyz */
+    uint32_t n_texcoords;  const float *texcoords;   /* uv  */
+    uint32_t n_normals;    const float *normals;     /* xyz */
+    const float *tangents;                           /* xyz per NORMAL index (mesh.h:115-117); NULL if no bump maps */
+
+    /* Mesh groups: the three index buffers of every MeshGroup concatenated; group g owns
+     * indices [group_first[g], group_first[g+1]) of each buffer (a multiple of 3). */
+    uint32_t n_groups;
+    const uint32_t *group_first;                     /* n_groups + 1 */
+    const uint32_t *idx_positions;
+    const uint32_t *idx_texcoords;
+    const uint32_t *idx_normals;
+    const int32_t  *group_material;                  /* per group; -1 == scene.default_mat (material 0 is NOT implied) */
+
+    /* BoundingHierarchy::spheres (pre-order, bsphere.cpp:328-350) and, per sphere, the mesh
+     * group it holds (BoundingHierarchy::mesh_groups / Scene::objects): -1 for internal nodes.
+     * Only the leaf visit ORDER (c1 subtree before c0, raytracer.cpp:208-209) is used by the
+     * GPU core, to reproduce the reference's first-encountered tie-break among equal-t hits;
+     * traversal runs on a GPU-built cluster hierarchy. */
+    uint32_t n_spheres;
+    const rt_bsphere *spheres;
+    const int32_t    *sphere_group;
+
+    uint32_t n_materials;  const rt_material *materials;
+    rt_material default_material;                    /* Scene::default_mat (main.cpp:579) */
+    uint32_t n_textures;   const rt_texture  *textures;
+    uint32_t n_lights;     const rt_light    *lights;  /* Scene::lights[0 .. light_count) */
+} rt_scene_desc;
+
+typedef struct rt_scene rt_scene;           /* opaque device-resident scene + GPU-built hierarchy */
+
+/* flags for rt_render* */
+#define RT_OUT_MEAN        0u               /* out = sum / samples, w = 1   (RenderPixel, main.cpp:262-263) */
+#define RT_OUT_SUM         1u               /* out = raw sample sum, w = number of samples (for sample-range splits) */
+#define RT_OUT_FULLFRAME   2u               /* device output is a W*H frame; pixel p is written at p, others untouched */
+#define RT_FLAG_COUNTERS   4u               /* also count sphere / cluster tests (slower) */
+#define RT_FLAG_TIME_KERNELS 8u             /* CUDA-event-time the trace kernels (adds events, no syncs) */
+#define RT_FLAG_ADAPTIVE   16u              /* run RenderPixel's adaptive second loop when min_samples < max_samples */
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+
+/* Copies every array of `desc` to device `device`, gathers per-triangle SoA records,
+ * builds the bounding-sphere cluster hierarchy on the GPU (replaces the per-ray use of
+ * BuildHierarchy's output, bsphere.cpp:379-444) and the host-computed decode tables
+ * (sRGB->linear, color.h:13-21; Hammersley directions, raytracer.cpp:273-341).
+ * The caller keeps ownership of its arrays. */
+int  rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene);
+void rt_scene_destroy(rt_scene *scene);
+
+/* Thread-local description of the last error on this thread ("" if none). */
+const char *rt_last_error(void);
+int  rt_abi_version(void);
+
+/* ---- Render / RenderTask / RenderPixel (main.cpp:224-358) ----------------------- */
+
+/* Renders pixels of a width x height frame and returns them in HOST memory, 4 floats per
+ * pixel, in the order of the pixel list. If pixel_ids is NULL the pixels are the linear
+ * row-major range [pixel_begin, pixel_begin + pixel_count) exactly like a RenderJob
+ * (main.cpp:316-317); otherwise pixel_ids[0 .. pixel_count) (pixel_begin ignored).
+ * Samples [sample_begin, sample_begin + sample_count) of every pixel are traced. */
+int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params *params,
+              uint32_t width, uint32_t height,
+              const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count,
+              uint32_t sample_begin, uint32_t sample_count, uint32_t flags,
+              float *out_rgba_host, rt_counters *out_counters);
+
+/* Same, output left in DEVICE memory (for the NCCL combine that replaces MPI_Gather,
+ * main.cpp:345-347). `stream` is a cudaStream_t (NULL = the scene's own stream); the call
+ * returns after enqueueing only when every wave could be scheduled without a host
+ * read-back, otherwise it synchronises `stream` internally. pixel_ids is a HOST pointer. */
+int rt_render_device(rt_scene *scene, const rt_camera *cam, const rt_params *params,
+                     uint32_t width, uint32_t height,
+                     const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count,
+                     uint32_t sample_begin, uint32_t sample_count, uint32_t flags,
+                     float *out_rgba_device, void *stream, rt_counters *out_counters);
+
+/* ---- TraceRay (raytracer.cpp:159-232) ------------------------------------------- */
+
+/* Closest hit for n arbitrary rays (host in, host out). any_hit != 0 runs the occlusion
+ * kernel used for ShadeLight's shadow rays (raytracer.cpp:385): only `hit` is defined. */
+int rt_trace_rays(rt_scene *scene, const rt_params *params, const rt_ray *rays, uint64_t n,
+                  int any_hit, rt_hit *out_hits, rt_counters *out_counters);
+
+/* Primary rays of RenderPixel's first loop (main.cpp:237-241) for the given pixels and
+ * samples: ray generation (Random_Seed + two jitter draws + MakeCameraRay) and closest hit.
+ * out_rays / out_hits hold pixel_count * sample_count entries, pixel-major. Either may be NULL. */
+int rt_trace_primary(rt_scene *scene, const rt_camera *cam, const rt_params *params,
+                     uint32_t width, uint32_t height,
+                     const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count,
+                     uint32_t sample_begin, uint32_t sample_count,
+                     rt_ray *out_rays, rt_hit *out_hits);
+
+/* ---- TraceRayColor (raytracer.cpp:413-577) -------------------------------------- */
+
+/* Radiance of n arbitrary rays with iters = params->bounce_depth; ray i draws from
+ * Random_Seed(seeds[i]). out_rgba: 4 floats per ray (w as the reference leaves it is not
+ * reproduced: w = 1 on hit paths is not guaranteed by the reference either; we return 0). */
+int rt_trace_color(rt_scene *scene, const rt_params *params, const rt_ray *rays,
+                   const uint64_t *seeds, uint64_t n, float *out_rgba, rt_counters *out_counters);
+
+/* ---- introspection --------------------------------------------------------------- */
+int rt_get_stats(const rt_scene *scene, rt_stats *out);
+
+/* GPU-built hierarchy facts: out[0]=triangles, [1]=clusters(leaves), [2]=nodes, [3]=max depth,
+ * [4]=bytes of node array, [5]=bytes of triangle records, [6]=build microseconds, [7]=reserved */
+int rt_get_hierarchy_info(const rt_scene *scene, uint64_t out[8]);
+
+/* Random_Seed + n x Random_Next on the device (random.h:9-42); KAT hook for the parity tests. */
+int rt_rng_kat(int device, uint64_t seed, uint32_t n, uint64_t *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H_ */
