@@ -223,10 +223,17 @@ int rt_render_device(rt_scene *scene, const rt_camera *cam, const rt_params *par
 
 /* ---- TraceRay (raytracer.cpp:159-232) ------------------------------------------- */
 
-/* Closest hit for n arbitrary rays (host in, host out). any_hit != 0 runs the occlusion
- * kernel used for ShadeLight's shadow rays (raytracer.cpp:385): only `hit` is defined. */
+/* TraceRay for n arbitrary rays (host in, host out). mode:
+ *   RT_TRACE_CLOSEST  closest hit, every rt_hit field as TraceRay leaves it;
+ *   RT_TRACE_ANY      the occlusion traversal used for ShadeLight's directional shadow rays
+ *                     (raytracer.cpp:385): only `hit` (TraceRay's bool) is meaningful;
+ *   RT_TRACE_BRUTE    closest hit by testing every triangle, no hierarchy (diagnostic: checks that
+ *                     the GPU hierarchy's pruning is conservative). */
+#define RT_TRACE_CLOSEST 0
+#define RT_TRACE_ANY     1
+#define RT_TRACE_BRUTE   2
 int rt_trace_rays(rt_scene *scene, const rt_params *params, const rt_ray *rays, uint64_t n,
-                  int any_hit, rt_hit *out_hits, rt_counters *out_counters);
+                  int mode, rt_hit *out_hits, rt_counters *out_counters);
 
 /* Primary rays of RenderPixel's first loop (main.cpp:237-241) for the given pixels and
  * samples: ray generation (Random_Seed + two jitter draws + MakeCameraRay) and closest hit.

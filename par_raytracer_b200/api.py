@@ -1,0 +1,172 @@
+"""Host-side mirror of the reference's render entry points over the C ABI (include/rt_b200.h).
+
+    Scene(scene_data)                          <-> main.cpp:546-599 (scene set-up; arrays stay the caller's)
+    Scene.render(cam, params, w, h)            <-> Render(Camera*, Scene*, u32, u32) -> Framebuffer   main.cpp:301-358
+    Scene.render_task(cam, params, w, h, a, b) <-> RenderTask(RenderJob*) over pixel range [a, b)     main.cpp:267-283
+    Scene.trace_rays(params, rays)             <-> TraceRay                                           raytracer.cpp:159-232
+    Scene.trace_color(params, rays, seeds)     <-> TraceRayColor                                      raytracer.cpp:413-577
+
+The shared library is the product; this module only marshals numpy arrays into it. If the library is
+missing or no GPU is present every compute call raises -- there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .cabi import RtSceneDesc, make_scene_desc
+from .types import CAMERA, COUNTERS, HIT, PARAMS, RAY, STATS, SceneData
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+
+RT_OUT_MEAN, RT_OUT_SUM, RT_OUT_FULLFRAME, RT_FLAG_COUNTERS = 0, 1, 2, 4
+RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
+
+EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
+           "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat"]
+
+
+class RtError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads librt_b200.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RtError(f"{LIB_PATH} is missing: run `python -m par_raytracer_b200.build` (nvcc, sm_100a). "
+                          "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.rt_last_error.restype = C.c_char_p
+        L.rt_scene_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.rt_scene_destroy.argtypes = [C.c_void_p]
+        L.rt_scene_destroy.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RtError(f"{what} failed ({rc}): {load_library().rt_last_error().decode()}")
+
+
+def rng_kat(seed: int, n: int, device: int = 0) -> np.ndarray:
+    out = np.zeros(n, np.uint64)
+    _check(load_library().rt_rng_kat(C.c_int(device), C.c_uint64(seed), C.c_uint32(n), _p(out)), "rt_rng_kat")
+    return out
+
+
+class Scene:
+    """Device-resident scene + GPU-built cluster hierarchy (rt_scene)."""
+
+    def __init__(self, scene: SceneData, device: int = 0):
+        self.lib = load_library()
+        self.data = scene
+        desc, keep = make_scene_desc(scene)
+        h = C.c_void_p()
+        _check(self.lib.rt_scene_create(C.addressof(desc), device, C.byref(h)), "rt_scene_create")
+        self.h = h
+        self.device = device
+        del keep
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rt_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- introspection ----------------------------------------------------------------------
+    def stats(self) -> np.ndarray:
+        s = np.zeros(1, STATS)
+        _check(self.lib.rt_get_stats(self.h, _p(s)), "rt_get_stats")
+        return s[0]
+
+    def hierarchy_info(self) -> dict:
+        o = np.zeros(8, np.uint64)
+        _check(self.lib.rt_get_hierarchy_info(self.h, _p(o)), "rt_get_hierarchy_info")
+        return dict(triangles=int(o[0]), nodes=int(o[2]), depth=int(o[3]), node_bytes=int(o[4]), triangle_bytes=int(o[5]),
+                    build_us=int(o[6]), build_iterations=int(o[7]))
+
+    # ---- Render / RenderTask ----------------------------------------------------------------
+    def render_task(self, cam, params, width, height, pixel_begin=0, pixel_count=None, pixel_ids=None, sample_begin=0,
+                    sample_count=None, flags=RT_OUT_MEAN):
+        cam = np.asarray(cam, CAMERA).reshape(1); params = np.asarray(params, PARAMS).reshape(1)
+        ids = None if pixel_ids is None else np.ascontiguousarray(pixel_ids, np.uint32)
+        if pixel_count is None:
+            pixel_count = len(ids) if ids is not None else width * height - pixel_begin
+        if sample_count is None:
+            sample_count = int(params[0]["min_samples"])
+        out = np.zeros((pixel_count, 4), np.float32)
+        cnt = np.zeros(1, COUNTERS)
+        _check(self.lib.rt_render(self.h, _p(cam), _p(params), C.c_uint32(width), C.c_uint32(height), _p(ids),
+                                  C.c_uint32(pixel_begin), C.c_uint32(pixel_count), C.c_uint32(sample_begin),
+                                  C.c_uint32(sample_count), C.c_uint32(flags), _p(out), _p(cnt)), "rt_render")
+        return out, cnt[0]
+
+    def render(self, cam, params, width, height, flags=RT_OUT_MEAN):
+        """Render(cam, scene, w, h): the whole frame, (h, w, 4) float32 linear HDR, w = 1."""
+        out, cnt = self.render_task(cam, params, width, height, 0, width * height, flags=flags)
+        return out.reshape(height, width, 4), cnt
+
+    def render_device(self, cam, params, width, height, out_ptr: int, pixel_begin=0, pixel_count=None, pixel_ids=None,
+                      sample_begin=0, sample_count=None, flags=RT_OUT_MEAN, stream: int = 0):
+        """Output left in device memory at `out_ptr` (e.g. a torch tensor's data_ptr())."""
+        cam = np.asarray(cam, CAMERA).reshape(1); params = np.asarray(params, PARAMS).reshape(1)
+        ids = None if pixel_ids is None else np.ascontiguousarray(pixel_ids, np.uint32)
+        if pixel_count is None:
+            pixel_count = len(ids) if ids is not None else width * height - pixel_begin
+        if sample_count is None:
+            sample_count = int(params[0]["min_samples"])
+        cnt = np.zeros(1, COUNTERS)
+        _check(self.lib.rt_render_device(self.h, _p(cam), _p(params), C.c_uint32(width), C.c_uint32(height), _p(ids),
+                                         C.c_uint32(pixel_begin), C.c_uint32(pixel_count), C.c_uint32(sample_begin),
+                                         C.c_uint32(sample_count), C.c_uint32(flags), C.c_void_p(out_ptr), C.c_void_p(stream),
+                                         _p(cnt)), "rt_render_device")
+        return cnt[0]
+
+    # ---- TraceRay / TraceRayColor -------------------------------------------------------------
+    def trace_rays(self, params, rays, mode=RT_TRACE_CLOSEST):
+        rays = np.ascontiguousarray(rays, RAY); params = np.asarray(params, PARAMS).reshape(1)
+        out = np.zeros(len(rays), HIT); cnt = np.zeros(1, COUNTERS)
+        _check(self.lib.rt_trace_rays(self.h, _p(params), _p(rays), C.c_uint64(len(rays)), C.c_int(mode), _p(out), _p(cnt)),
+               "rt_trace_rays")
+        return out, cnt[0]
+
+    def trace_primary(self, cam, params, width, height, pixel_ids=None, pixel_begin=0, pixel_count=None, sample_begin=0,
+                      sample_count=1, want_rays=True, want_hits=True):
+        cam = np.asarray(cam, CAMERA).reshape(1); params = np.asarray(params, PARAMS).reshape(1)
+        ids = None if pixel_ids is None else np.ascontiguousarray(pixel_ids, np.uint32)
+        if pixel_count is None:
+            pixel_count = len(ids) if ids is not None else width * height - pixel_begin
+        n = pixel_count * sample_count
+        rays = np.zeros(n, RAY) if want_rays else None
+        hits = np.zeros(n, HIT) if want_hits else None
+        _check(self.lib.rt_trace_primary(self.h, _p(cam), _p(params), C.c_uint32(width), C.c_uint32(height), _p(ids),
+                                         C.c_uint32(pixel_begin), C.c_uint32(pixel_count), C.c_uint32(sample_begin),
+                                         C.c_uint32(sample_count), _p(rays), _p(hits)), "rt_trace_primary")
+        return rays, hits
+
+    def trace_color(self, params, rays, seeds):
+        rays = np.ascontiguousarray(rays, RAY); seeds = np.ascontiguousarray(seeds, np.uint64)
+        params = np.asarray(params, PARAMS).reshape(1)
+        out = np.zeros((len(rays), 4), np.float32); cnt = np.zeros(1, COUNTERS)
+        _check(self.lib.rt_trace_color(self.h, _p(params), _p(rays), _p(seeds), C.c_uint64(len(rays)), _p(out), _p(cnt)),
+               "rt_trace_color")
+        return out, cnt[0]

@@ -1,0 +1,869 @@
+// rt_api.cu -- the C ABI of include/rt_b200.h: scene upload, GPU hierarchy build, wave scheduling.
+// Host code in this file only moves data, sizes launches and builds small decode tables; every hit,
+// ray and colour is computed by the kernels in rt_trace.cuh / rt_shade.cuh. There is no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_build.cuh"
+#include "rt_common.cuh"
+#include "rt_rng.cuh"
+#include "rt_shade.cuh"
+#include "rt_trace.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define CKL(name)                                                                                         \
+    do {                                                                                                  \
+        cudaError_t e_ = cudaGetLastError();                                                              \
+        if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, "launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *rt_last_error(void) { return g_err.c_str(); }
+extern "C" int rt_abi_version(void) { return RT_ABI_VERSION; }
+
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// device buffer bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct DevArena {
+    std::vector<void *> ptrs;
+    template <typename T> cudaError_t alloc(T **p, size_t n) {
+        *p = nullptr;
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    void release() {
+        for (void *p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+struct WaveTotals { unsigned long long closest, shadow, waves, pad; };
+
+struct Pool {                 // per-render working set, kept between calls and grown on demand
+    DevArena mem;
+    uint32_t capacity = 0, depth = 0, lights = 0;
+    PathPool paths{};
+    RayQueue q[2]{};
+    HitRec *hits = nullptr;
+    ShadowQueue shadow{};
+    uint32_t *counts = nullptr;        // [0],[1]: ray queue sizes (ping-pong), [2]: shadow queue size
+    WaveTotals *totals = nullptr;
+    TraceCounters *tcount = nullptr;
+    uint32_t *h_counts = nullptr;      // pinned mirror of counts
+};
+
+struct rt_scene {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevArena mem;
+    DevScene d{};
+    std::vector<float> spec_intensity;   // per material (+ default), for the Phong-lobe table
+    float4 *spec_dir = nullptr;
+    uint32_t spec_dir_ss = 0;
+    uint32_t n_lights = 0;
+    uint64_t info[8] = {0};
+    rt_stats stats{};
+    Pool pool;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+};
+
+// ---------------------------------------------------------------------------------------------
+// host-built decode tables (the only libm calls of the product; same glibc the reference would use)
+// ---------------------------------------------------------------------------------------------
+#define RT_PI32 (3.1415927f)                                   // brt.h:23
+
+static float host_radical_inverse(uint32_t bits) {             // raytracer.cpp:273-282
+    bits = (bits << 16u) | (bits >> 16u);
+    bits = ((bits & 0x55555555u) << 1u) | ((bits & 0xAAAAAAAAu) >> 1u);
+    bits = ((bits & 0x33333333u) << 2u) | ((bits & 0xCCCCCCCCu) >> 2u);
+    bits = ((bits & 0x0F0F0F0Fu) << 4u) | ((bits & 0xF0F0F0F0u) >> 4u);
+    bits = ((bits & 0x00FF00FFu) << 8u) | ((bits & 0xFF00FF00u) >> 8u);
+    return (float)(bits * 2.3283064365386963e-10);
+}
+
+static void host_srgb_lut(float *lut) {                        // color.h:13-21 over texture.cpp:44-48's 256 inputs
+    const float one_over_255 = 1.0f / 255.0f;
+    for (int i = 0; i < 256; ++i) {
+        volatile float srgb = (float)i * one_over_255;
+        lut[i] = srgb <= 0.04045f ? srgb / 12.92f : powf((srgb + 0.055f) / 1.055f, 2.4f);
+    }
+}
+
+static void host_hammersley_dirs(float4 *out) {                // raytracer.cpp:284-288 + 322-328 for i in [0, 1024)
+    for (uint32_t i = 0; i < 1024; ++i) {
+        volatile float xi_x = (float)i / (float)1024u;
+        volatile float xi_y = host_radical_inverse(i);
+        volatile float phi = xi_y * 2.0f * RT_PI32;
+        volatile float cp = cosf(phi);
+        volatile float sp = sinf(phi);
+        volatile float ct = sqrtf(1.0f - xi_x);
+        volatile float st = sqrtf(1.0f - ct * ct);
+        out[i] = make_float4(cp * st, sp * st, ct, 0.0f);
+    }
+}
+
+static void host_phong_dirs(const std::vector<float> &spec_intensity, uint32_t ss, std::vector<float4> &out) {   // raytracer.cpp:290-300
+    out.resize(spec_intensity.size() * (size_t)std::max(1u, ss));
+    for (size_t m = 0; m < spec_intensity.size(); ++m) {
+        for (uint32_t s = 0; s < ss; ++s) {
+            volatile float xi_x = (float)s / (float)ss;
+            volatile float xi_y = host_radical_inverse(s);
+            volatile float phi = 2.0f * RT_PI32 * xi_x;
+            volatile float cp = cosf(phi);
+            volatile float sp = sinf(phi);
+            volatile float ct = powf(1.0f - xi_y, 1.0f / (spec_intensity[m] + 1.0f));
+            volatile float st = sqrtf(1.0f - (ct * ct));
+            out[m * ss + s] = make_float4(cp * st, sp * st, ct, 0.0f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hierarchy build orchestration (kernels in rt_build.cuh)
+// ---------------------------------------------------------------------------------------------
+static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInput &gin, bool has_tangents) {
+    cudaStream_t st = sc->stream;
+    const uint32_t n = bin.n_tris;
+    DevArena tmp;
+    auto done = [&](int rc) { tmp.release(); return rc; };
+#define CKB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+#define CKLB(name) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_))); } while (0)
+
+    cudaEvent_t e0, e1;
+    CKB(cudaEventCreate(&e0)); CKB(cudaEventCreate(&e1));
+    CKB(cudaEventRecord(e0, st));
+
+    // final arrays
+    TriRec *tris; uint32_t *tri_rank, *tri_vertex0; int32_t *tri_object; float4 *tri_uv, *tri_nrm, *tri_tan = nullptr;
+    CKB(sc->mem.alloc(&tris, n)); CKB(sc->mem.alloc(&tri_rank, n)); CKB(sc->mem.alloc(&tri_vertex0, n));
+    CKB(sc->mem.alloc(&tri_object, n)); CKB(sc->mem.alloc(&tri_uv, 2 * (size_t)n)); CKB(sc->mem.alloc(&tri_nrm, 3 * (size_t)n));
+    if (has_tangents) CKB(sc->mem.alloc(&tri_tan, 3 * (size_t)n));
+
+    uint32_t n_pad = BITONIC_TILE;
+    while (n_pad < n) n_pad <<= 1;
+    float4 *tri_sphere; uint32_t *bounds; uint64_t *keys; uint32_t *vals;
+    CKB(tmp.alloc(&tri_sphere, n)); CKB(tmp.alloc(&bounds, 8)); CKB(tmp.alloc(&keys, n_pad)); CKB(tmp.alloc(&vals, n_pad));
+    {
+        uint32_t hb[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
+        CKB(cudaMemcpyAsync(bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
+    }
+    k_tri_spheres<<<cdiv(n, 256), 256, 0, st>>>(bin, tri_sphere, bounds); CKLB("k_tri_spheres");
+    k_morton<<<cdiv(n_pad, 256), 256, 0, st>>>(n, n_pad, tri_sphere, bounds, keys, vals); CKLB("k_morton");
+    // bitonic sort
+    k_bitonic_shared<<<n_pad / BITONIC_TILE, 1024, 0, st>>>(keys, vals, 2, BITONIC_TILE, 0); CKLB("k_bitonic_shared");
+    for (uint64_t k = 2ull * BITONIC_TILE; k <= n_pad; k <<= 1) {
+        for (uint32_t j = (uint32_t)(k >> 1); j >= BITONIC_TILE; j >>= 1) {
+            k_bitonic_global<<<cdiv(n_pad, 256), 256, 0, st>>>(keys, vals, n_pad, j, (uint32_t)k); CKLB("k_bitonic_global");
+        }
+        k_bitonic_shared<<<n_pad / BITONIC_TILE, 1024, 0, st>>>(keys, vals, (uint32_t)k, (uint32_t)k, 1); CKLB("k_bitonic_shared");
+    }
+
+    // temp tree
+    const uint32_t n_total = 2 * n - 1;
+    TempTree t;
+    CKB(tmp.alloc(&t.c0, n_total)); CKB(tmp.alloc(&t.c1, n_total)); CKB(tmp.alloc(&t.parent, n_total));
+    CKB(tmp.alloc(&t.size, n_total)); CKB(tmp.alloc(&t.kept, n_total)); CKB(tmp.alloc(&t.sphere, n_total));
+    float4 *cs[2]; int32_t *cn[2]; uint32_t *nn; uint64_t *flags, *scan, *bsums, *total;
+    CKB(tmp.alloc(&cs[0], n)); CKB(tmp.alloc(&cs[1], n)); CKB(tmp.alloc(&cn[0], n)); CKB(tmp.alloc(&cn[1], n));
+    CKB(tmp.alloc(&nn, n)); CKB(tmp.alloc(&flags, n)); CKB(tmp.alloc(&scan, n));
+    CKB(tmp.alloc(&bsums, cdiv(n, SCAN_TILE) + 1)); CKB(tmp.alloc(&total, 1));
+    uint32_t *tri_offset, *kept_index, *max_depth;
+    CKB(tmp.alloc(&tri_offset, n_total)); CKB(tmp.alloc(&kept_index, n_total)); CKB(tmp.alloc(&max_depth, 1));
+
+    uint32_t kept_nodes = 0, depth = 0, iterations = 0;
+    int32_t root_temp = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int pair_mode = attempt;       // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n)
+        k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, cs[0], cn[0], t); CKLB("k_ploc_init");
+        uint32_t m = n, created = 0;
+        int cur = 0;
+        iterations = 0;
+        while (m > 1) {
+            k_ploc_nn<<<cdiv(m, 256), 256, 0, st>>>(m, cs[cur], nn, pair_mode); CKLB("k_ploc_nn");
+            k_ploc_flags<<<cdiv(m, 256), 256, 0, st>>>(m, nn, flags); CKLB("k_ploc_flags");
+            uint32_t nb = cdiv(m, SCAN_TILE);
+            k_scan_reduce<<<nb, SCAN_BLOCK, 0, st>>>(flags, m, bsums); CKLB("k_scan_reduce");
+            k_scan_blocksums<<<1, 1024, 0, st>>>(bsums, nb, total); CKLB("k_scan_blocksums");
+            k_scan_apply<<<nb, SCAN_BLOCK, 0, st>>>(flags, m, bsums, scan); CKLB("k_scan_apply");
+            k_ploc_merge<<<cdiv(m, 256), 256, 0, st>>>(m, n, created, nn, flags, scan, cs[cur], cn[cur], cs[cur ^ 1], cn[cur ^ 1], t);
+            CKLB("k_ploc_merge");
+            uint64_t h_total = 0;
+            CKB(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, st));
+            CKB(cudaStreamSynchronize(st));
+            uint32_t merges = (uint32_t)(h_total >> 32), valid = (uint32_t)(h_total & 0xffffffffull);
+            if (merges == 0 || valid != m - merges) return done(fail(RT_ERR_STATE, "hierarchy build made no progress (m=%u merges=%u valid=%u)", m, merges, valid));
+            created += merges;
+            m = valid;
+            cur ^= 1;
+            iterations++;
+        }
+        CKB(cudaMemcpyAsync(&root_temp, cn[cur], 4, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemsetAsync(max_depth, 0, 4, st));
+        k_layout<<<cdiv(n_total, 256), 256, 0, st>>>(n_total, t, tri_offset, kept_index, max_depth); CKLB("k_layout");
+        CKB(cudaMemcpyAsync(&depth, max_depth, 4, cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemcpyAsync(&kept_nodes, t.kept + (n_total - 1), 4, cudaMemcpyDeviceToHost, st));
+        CKB(cudaStreamSynchronize(st));
+        if (root_temp != (int32_t)(n_total - 1) && n > 1) return done(fail(RT_ERR_STATE, "hierarchy root mismatch"));
+        if (depth + 2 <= RT_STACK_MAX) break;
+        if (attempt == 1) return done(fail(RT_ERR_STATE, "hierarchy depth %u exceeds traversal stack", depth));
+    }
+
+    HNode *nodes;
+    CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
+    if (kept_nodes > 0) {
+        k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes); CKLB("k_emit_nodes");
+        sc->d.root = 0;
+    } else {
+        sc->d.root = -(int)(1u + 0u * 8u + n);     // the whole scene is one cluster (n <= RT_LEAF_MAX)
+    }
+    k_gather<<<cdiv(n, 256), 256, 0, st>>>(gin, vals, tri_offset, tris, tri_rank, tri_uv, tri_nrm, tri_tan, tri_vertex0, tri_object);
+    CKLB("k_gather");
+    CKB(cudaEventRecord(e1, st));
+    CKB(cudaStreamSynchronize(st));
+    float ms = 0;
+    CKB(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+
+    sc->d.nodes = nodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
+    sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object;
+    sc->d.n_tris = n; sc->d.n_nodes = kept_nodes;
+    sc->info[0] = n; sc->info[1] = 0; sc->info[2] = kept_nodes; sc->info[3] = depth;
+    sc->info[4] = (uint64_t)kept_nodes * sizeof(HNode); sc->info[5] = (uint64_t)n * sizeof(TriRec);
+    sc->info[6] = (uint64_t)(ms * 1000.0f); sc->info[7] = iterations;
+    return done(RT_OK);
+#undef CKB
+#undef CKLB
+}
+
+// ---------------------------------------------------------------------------------------------
+// rt_scene_create / destroy
+// ---------------------------------------------------------------------------------------------
+template <typename T> static cudaError_t upload(DevArena &a, cudaStream_t st, T **dst, const T *src, size_t n) {
+    cudaError_t e = a.alloc(dst, n);
+    if (e != cudaSuccess) return e;
+    if (n && src) e = cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+extern "C" void rt_scene_destroy(rt_scene *sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    if (sc->stream) cudaStreamSynchronize(sc->stream);
+    sc->pool.mem.release();
+    if (sc->pool.h_counts) cudaFreeHost(sc->pool.h_counts);
+    sc->mem.release();
+    if (sc->ev0) cudaEventDestroy(sc->ev0);
+    if (sc->ev1) cudaEventDestroy(sc->ev1);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    delete sc;
+}
+
+extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene) {
+    g_err.clear();
+    if (!desc || !out_scene) return fail(RT_ERR_ARG, "null argument");
+    *out_scene = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RT_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    const uint32_t G = desc->n_groups;
+    if (G && (!desc->group_first || !desc->idx_positions || !desc->idx_texcoords || !desc->idx_normals || !desc->group_material))
+        return fail(RT_ERR_ARG, "group arrays missing");
+    const uint64_t n_idx = G ? desc->group_first[G] : 0;
+    if (n_idx % 3) return fail(RT_ERR_ARG, "index count %llu not a multiple of 3", (unsigned long long)n_idx);
+    if (n_idx / 3 > 200000000ull) return fail(RT_ERR_ARG, "too many triangles");
+    const uint32_t n_tris = (uint32_t)(n_idx / 3);
+    for (uint32_t g = 0; g < G; ++g)
+        if (desc->group_first[g + 1] < desc->group_first[g] || (desc->group_first[g + 1] - desc->group_first[g]) % 3)
+            return fail(RT_ERR_ARG, "group %u index range invalid", g);
+    if (n_tris && (!desc->positions || !desc->texcoords || !desc->normals)) return fail(RT_ERR_ARG, "vertex streams missing");
+    for (uint64_t i = 0; i < n_idx; ++i) {
+        if (desc->idx_positions[i] >= desc->n_positions || desc->idx_texcoords[i] >= desc->n_texcoords ||
+            desc->idx_normals[i] >= desc->n_normals)
+            return fail(RT_ERR_ARG, "vertex index out of range at %llu", (unsigned long long)i);
+    }
+    CK(cudaSetDevice(device));
+    rt_scene *sc = new rt_scene;
+    sc->device = device;
+    auto bail = [&](int rc) { rt_scene_destroy(sc); return rc; };
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    CKS(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+    CKS(cudaEventCreate(&sc->ev0)); CKS(cudaEventCreate(&sc->ev1));
+    CKS(cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t st = sc->stream;
+
+    // ---- tie-break ranks: the reference's leaf encounter order (raytracer.cpp:168-172, 208-209) ----
+    std::vector<uint32_t> rank_base(G ? G : 1, 0);
+    std::vector<int32_t> group_object(G ? G : 1, -1);
+    {
+        std::vector<char> seen(G ? G : 1, 0);
+        uint32_t running = 0;
+        if (desc->n_spheres && desc->spheres && desc->sphere_group) {
+            std::vector<uint32_t> stack; stack.push_back(0);
+            uint64_t guard = 0;
+            while (!stack.empty()) {
+                uint32_t i = stack.back(); stack.pop_back();
+                if (i >= desc->n_spheres || ++guard > 4ull * desc->n_spheres + 8) return bail(fail(RT_ERR_ARG, "malformed sphere hierarchy"));
+                const rt_bsphere &s = desc->spheres[i];
+                if (s.c0 && s.c1) { stack.push_back(s.c0); stack.push_back(s.c1); }
+                else {
+                    int32_t g = desc->sphere_group[i];
+                    if (g < 0 || (uint32_t)g >= G || seen[g]) return bail(fail(RT_ERR_ARG, "sphere %u: bad mesh group %d", i, g));
+                    seen[g] = 1; rank_base[g] = running; group_object[g] = (int32_t)i;
+                    running += (desc->group_first[g + 1] - desc->group_first[g]) / 3;
+                }
+            }
+            for (uint32_t g = 0; g < G; ++g) if (!seen[g]) return bail(fail(RT_ERR_ARG, "mesh group %u is in no leaf sphere", g));
+        } else {
+            for (uint32_t g = 0; g < G; ++g) { rank_base[g] = running; group_object[g] = (int32_t)g; running += (desc->group_first[g + 1] - desc->group_first[g]) / 3; }
+        }
+    }
+    std::vector<int32_t> group_mat(G ? G : 1, 0);
+    for (uint32_t g = 0; g < G; ++g) {
+        int32_t m = desc->group_material[g];
+        if (m >= (int32_t)desc->n_materials) return bail(fail(RT_ERR_ARG, "group %u material %d out of range", g, m));
+        group_mat[g] = m < 0 ? (int32_t)desc->n_materials : m;
+    }
+
+    // ---- materials / textures / lights ----
+    std::vector<DevMaterial> mats(desc->n_materials + 1);
+    sc->spec_intensity.resize(desc->n_materials + 1);
+    bool any_bump = false;
+    for (uint32_t i = 0; i <= desc->n_materials; ++i) {
+        const rt_material &m = i < desc->n_materials ? desc->materials[i] : desc->default_material;
+        DevMaterial &d = mats[i];
+        memset(&d, 0, sizeof(d));
+        d.specular_intensity = m.specular_intensity; d.index_of_refraction = m.index_of_refraction; d.alpha = m.alpha;
+        for (int k = 0; k < 3; ++k) { d.ambient[k] = m.ambient_color[k]; d.diffuse[k] = m.diffuse_color[k]; d.specular[k] = m.specular_color[k]; }
+        d.tex_ambient = m.ambient_texture; d.tex_diffuse = m.diffuse_texture; d.tex_specular = m.specular_texture;
+        d.tex_alpha = m.alpha_texture; d.tex_bump = m.bump_texture;
+        const int32_t *tx[5] = {&d.tex_ambient, &d.tex_diffuse, &d.tex_specular, &d.tex_alpha, &d.tex_bump};
+        for (int k = 0; k < 5; ++k) if (*tx[k] >= (int32_t)desc->n_textures) return bail(fail(RT_ERR_ARG, "material %u texture index out of range", i));
+        if (d.tex_bump >= 0) any_bump = true;
+        sc->spec_intensity[i] = m.specular_intensity;
+    }
+    if (any_bump && !desc->tangents) return bail(fail(RT_ERR_ARG, "bump-mapped material but no tangents"));
+    std::vector<DevTexture> texs(desc->n_textures ? desc->n_textures : 1);
+    std::vector<uint8_t> blob;
+    for (uint32_t i = 0; i < desc->n_textures; ++i) {
+        const rt_texture &t = desc->textures[i];
+        if (!t.texels || t.channels < 1 || t.channels > 4 || t.size_x < 2 || t.size_y < 2) return bail(fail(RT_ERR_ARG, "texture %u invalid", i));
+        texs[i].size_x = t.size_x; texs[i].size_y = t.size_y; texs[i].channels = t.channels; texs[i].offset = (uint32_t)blob.size();
+        size_t bytes = (size_t)t.size_x * t.size_y * t.channels;
+        if (blob.size() + bytes > 0xFFFFFFFFull) return bail(fail(RT_ERR_ARG, "textures exceed 4 GiB"));
+        blob.insert(blob.end(), t.texels, t.texels + bytes);
+    }
+    std::vector<DevLight> lights(desc->n_lights ? desc->n_lights : 1);
+    for (uint32_t i = 0; i < desc->n_lights; ++i) {
+        const rt_light &l = desc->lights[i];
+        DevLight &d = lights[i];
+        memset(&d, 0, sizeof(d));
+        if (l.type != RT_LIGHT_DIRECTIONAL && l.type != RT_LIGHT_POINT) return bail(fail(RT_ERR_ARG, "light %u: unrecognised type %d", i, l.type));
+        d.type = l.type; d.falloff = l.falloff;
+        for (int k = 0; k < 3; ++k) { d.color[k] = l.color[k]; d.position[k] = l.position[k]; d.facing[k] = l.facing[k]; }
+    }
+    sc->n_lights = desc->n_lights;
+
+    DevMaterial *d_mats; DevTexture *d_texs; uint8_t *d_blob; DevLight *d_lights; float *d_lut; float4 *d_hamm;
+    CKS(upload(sc->mem, st, &d_mats, mats.data(), mats.size()));
+    CKS(upload(sc->mem, st, &d_texs, texs.data(), texs.size()));
+    CKS(upload(sc->mem, st, &d_blob, blob.data(), blob.size()));
+    CKS(upload(sc->mem, st, &d_lights, lights.data(), lights.size()));
+    float lut[256]; host_srgb_lut(lut);
+    std::vector<float4> hamm(1024); host_hammersley_dirs(hamm.data());
+    CKS(upload(sc->mem, st, &d_lut, lut, 256));
+    CKS(upload(sc->mem, st, &d_hamm, hamm.data(), 1024));
+    sc->d.materials = d_mats; sc->d.textures = d_texs; sc->d.texels = d_blob; sc->d.lights = d_lights;
+    sc->d.srgb_lut = d_lut; sc->d.hamm_dir = d_hamm; sc->d.spec_dir = nullptr;
+    sc->d.n_materials = desc->n_materials; sc->d.n_lights = desc->n_lights;
+    sc->stats.h2d_bytes = mats.size() * sizeof(DevMaterial) + blob.size();
+
+    // ---- geometry: upload the reference's arrays as they are, build on the GPU ----
+    sc->d.n_tris = 0; sc->d.root = 0;
+    if (n_tris) {
+        DevArena in;     // input arrays are only needed during the build
+        auto bail2 = [&](int rc) { in.release(); return bail(rc); };
+#define CKI(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail2(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+        float *d_pos, *d_tc, *d_nrm, *d_tan = nullptr; uint32_t *d_ip, *d_it, *d_in, *d_gf, *d_rb; int32_t *d_go, *d_gm;
+        CKI(upload(in, st, &d_pos, desc->positions, 3 * (size_t)desc->n_positions));
+        CKI(upload(in, st, &d_tc, desc->texcoords, 2 * (size_t)desc->n_texcoords));
+        CKI(upload(in, st, &d_nrm, desc->normals, 3 * (size_t)desc->n_normals));
+        if (any_bump) CKI(upload(in, st, &d_tan, desc->tangents, 3 * (size_t)desc->n_normals));
+        CKI(upload(in, st, &d_ip, desc->idx_positions, (size_t)n_idx));
+        CKI(upload(in, st, &d_it, desc->idx_texcoords, (size_t)n_idx));
+        CKI(upload(in, st, &d_in, desc->idx_normals, (size_t)n_idx));
+        CKI(upload(in, st, &d_gf, desc->group_first, (size_t)G + 1));
+        CKI(upload(in, st, &d_rb, rank_base.data(), (size_t)G));
+        CKI(upload(in, st, &d_go, group_object.data(), (size_t)G));
+        CKI(upload(in, st, &d_gm, group_mat.data(), (size_t)G));
+        sc->stats.h2d_bytes += 4ull * (3ull * desc->n_positions + 2ull * desc->n_texcoords + 3ull * desc->n_normals * (any_bump ? 2 : 1) + 3ull * n_idx);
+        BuildInput bin; bin.positions = d_pos; bin.idx_positions = d_ip; bin.group_first = d_gf; bin.n_groups = G; bin.n_tris = n_tris;
+        GatherInput gin; gin.positions = d_pos; gin.texcoords = d_tc; gin.normals = d_nrm; gin.tangents = d_tan;
+        gin.idx_p = d_ip; gin.idx_t = d_it; gin.idx_n = d_in; gin.group_first = d_gf; gin.group_rank_base = d_rb;
+        gin.group_object = d_go; gin.group_material = d_gm; gin.n_groups = G; gin.n_tris = n_tris;
+        int rc = build_hierarchy(sc, bin, gin, any_bump);
+        if (rc != RT_OK) return bail2(rc);
+        in.release();
+#undef CKI
+    }
+    CKS(cudaStreamSynchronize(st));
+#undef CKS
+    *out_scene = sc;
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool
+// ---------------------------------------------------------------------------------------------
+static uint32_t pool_limit() {
+    const char *e = getenv("RT_B200_POOL");
+    uint32_t v = e ? (uint32_t)strtoul(e, nullptr, 10) : 0;
+    return v ? v : (1u << 22);
+}
+
+static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
+    Pool &p = sc->pool;
+    uint32_t lights = std::max(1u, sc->n_lights);
+    depth = std::max(1u, depth);
+    if (p.capacity >= capacity && p.depth >= depth && p.lights >= lights) return RT_OK;
+    CK(cudaStreamSynchronize(sc->stream));
+    p.mem.release();
+    capacity = std::max(capacity, p.capacity); depth = std::max(depth, p.depth);
+    p.capacity = p.depth = 0;
+    size_t c = capacity;
+    CK(p.mem.alloc(&p.paths.rng_cur, c)); CK(p.mem.alloc(&p.paths.rng_x, c)); CK(p.mem.alloc(&p.paths.rng_seed, c));
+    CK(p.mem.alloc(&p.paths.rng_n, c)); CK(p.mem.alloc(&p.paths.acc, c)); CK(p.mem.alloc(&p.paths.node_T, c));
+    CK(p.mem.alloc(&p.paths.sp, c)); CK(p.mem.alloc(&p.paths.frames, c * RT_FRAME_F4 * depth));
+    p.paths.capacity = capacity;
+    for (int k = 0; k < 2; ++k) { CK(p.mem.alloc(&p.q[k].o, c)); CK(p.mem.alloc(&p.q[k].d, c)); }
+    CK(p.mem.alloc(&p.hits, c));
+    CK(p.mem.alloc(&p.shadow.q.o, c * lights)); CK(p.mem.alloc(&p.shadow.q.d, c * lights)); CK(p.mem.alloc(&p.shadow.rad, c * lights));
+    CK(p.mem.alloc(&p.counts, 4)); CK(p.mem.alloc(&p.totals, 1)); CK(p.mem.alloc(&p.tcount, 1));
+    p.shadow.count = p.counts + 2;
+    if (!p.h_counts) CK(cudaMallocHost((void **)&p.h_counts, 64));
+    p.capacity = capacity; p.depth = depth; p.lights = lights;
+    return RT_OK;
+}
+
+static int ensure_spec_table(rt_scene *sc, uint32_t ss) {
+    if (sc->spec_dir && sc->spec_dir_ss == ss) return RT_OK;
+    std::vector<float4> tab;
+    host_phong_dirs(sc->spec_intensity, ss, tab);
+    CK(cudaStreamSynchronize(sc->stream));
+    float4 *d;
+    CK(sc->mem.alloc(&d, tab.size()));
+    CK(cudaMemcpyAsync(d, tab.data(), tab.size() * sizeof(float4), cudaMemcpyHostToDevice, sc->stream));
+    CK(cudaStreamSynchronize(sc->stream));
+    sc->spec_dir = d; sc->spec_dir_ss = ss; sc->d.spec_dir = d;
+    return RT_OK;
+}
+
+static DevParams to_dev_params(const rt_params *p) {
+    DevParams d;
+    d.ray_bias = p->ray_bias; d.reflection_samples = p->reflection_samples; d.spec_samples = p->spec_samples;
+    d.bounce_depth = p->bounce_depth; d.bg[0] = p->background_color[0]; d.bg[1] = p->background_color[1];
+    d.bg[2] = p->background_color[2]; d.pad = 0; d.base_seed = p->base_seed;
+    return d;
+}
+
+static int check_params(const rt_params *p) {
+    if (!p) return fail(RT_ERR_ARG, "params is null");
+    if (p->bounce_depth > 200) return fail(RT_ERR_ARG, "bounce_depth %u > 200", p->bounce_depth);
+    if (p->reflection_samples + p->spec_samples > 1000000u) return fail(RT_ERR_ARG, "too many reflection samples");
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the wave loop: runs every live path of the pool to completion
+// ---------------------------------------------------------------------------------------------
+struct WaveCfg { bool count; };
+
+static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint32_t flags, uint64_t *launches) {
+    Pool &p = sc->pool;
+    cudaStream_t st = sc->stream;
+    const bool count = (flags & RT_FLAG_COUNTERS) != 0;
+    const int use_atomics = sc->n_lights > 1 ? 1 : 0;
+    const uint32_t max_grid = (uint32_t)sc->sm_count * 16u;
+    uint32_t n = n_first;
+    int cur = 0;
+    while (n > 0) {
+        CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
+        CK(cudaMemsetAsync(p.counts + 2, 0, 4, st));
+        uint32_t grid = std::min(cdiv(n, 128), max_grid);
+        if (count) k_trace_closest<true><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[cur], p.counts + cur, n, p.hits, p.tcount);
+        else k_trace_closest<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[cur], p.counts + cur, n, p.hits, p.tcount);
+        CKL("k_trace_closest");
+        k_logic<<<cdiv(n, 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, n, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
+        CKL("k_logic");
+        CK(cudaMemcpyAsync(p.h_counts, p.counts, 16, cudaMemcpyDeviceToHost, st));
+        uint32_t n_sh_max = n * std::max(1u, sc->n_lights);
+        uint32_t sgrid = std::min(cdiv(n_sh_max, 128), max_grid);
+        if (sc->n_lights) {
+            if (count) k_trace_shadow<true><<<sgrid, 128, 0, st>>>(sc->d, prm.ray_bias, p.shadow.q, p.shadow.rad, p.shadow.count, n_sh_max, p.paths.acc, use_atomics, p.tcount);
+            else k_trace_shadow<false><<<sgrid, 128, 0, st>>>(sc->d, prm.ray_bias, p.shadow.q, p.shadow.rad, p.shadow.count, n_sh_max, p.paths.acc, use_atomics, p.tcount);
+            CKL("k_trace_shadow");
+            *launches += 1;
+        }
+        *launches += 2;
+        CK(cudaStreamSynchronize(st));
+        sc->stats.closest_rays += n;
+        sc->stats.shadow_rays += p.h_counts[2];
+        sc->stats.waves += 1;
+        n = p.h_counts[cur ^ 1];
+        cur ^= 1;
+    }
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rt_render_device / rt_render
+// ---------------------------------------------------------------------------------------------
+static DevCamera to_dev_camera(const rt_camera *c) {
+    DevCamera d;
+    static_assert(sizeof(DevCamera) == sizeof(rt_camera), "camera layout");
+    memcpy(&d, c, sizeof(d));
+    return d;
+}
+
+static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height,
+                       const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count, uint32_t sample_begin,
+                       uint32_t sample_count, uint32_t flags, float *out_dev, cudaStream_t user_stream, rt_counters *out_counters) {
+    if (!sc || !cam || !out_dev) return fail(RT_ERR_ARG, "null argument");
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (!width || !height) return fail(RT_ERR_ARG, "empty frame");
+    const uint64_t frame = (uint64_t)width * height;
+    if (!pixel_ids && (uint64_t)pixel_begin + pixel_count > frame) return fail(RT_ERR_ARG, "pixel range exceeds the frame");
+    if (pixel_ids) for (uint32_t k = 0; k < pixel_count; ++k) if (pixel_ids[k] >= frame) return fail(RT_ERR_ARG, "pixel id %u out of range", pixel_ids[k]);
+    CK(cudaSetDevice(sc->device));
+    cudaStream_t st = sc->stream;
+    if (user_stream) {      // order after the caller's stream
+        CK(cudaEventRecord(sc->ev1, user_stream));
+        CK(cudaStreamWaitEvent(st, sc->ev1, 0));
+    }
+    memset(&sc->stats, 0, sizeof(sc->stats));
+    uint64_t launches = 0;
+    if (pixel_count == 0 || sample_count == 0) { if (out_counters) memset(out_counters, 0, sizeof(*out_counters)); return RT_OK; }
+
+    DevParams prm = to_dev_params(params);
+    DevCamera dcam = to_dev_camera(cam);
+    rc = ensure_spec_table(sc, params->spec_samples);
+    if (rc) return rc;
+    const uint32_t limit = pool_limit();
+    const uint32_t spp_chunk = std::min(sample_count, limit);
+    const uint32_t pix_per_batch = std::max(1u, std::min(pixel_count, limit / spp_chunk));
+    rc = ensure_pool(sc, (uint32_t)std::min<uint64_t>((uint64_t)pix_per_batch * spp_chunk, (uint64_t)limit), params->bounce_depth);
+    if (rc) return rc;
+    Pool &p = sc->pool;
+
+    DevArena tmp;
+    auto done = [&](int r) { tmp.release(); return r; };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    float4 *accum; uint32_t *d_ids = nullptr;
+    CKR(tmp.alloc(&accum, pixel_count));
+    CKR(cudaMemsetAsync(accum, 0, (size_t)pixel_count * sizeof(float4), st));
+    if (pixel_ids) {
+        CKR(tmp.alloc(&d_ids, pixel_count));
+        CKR(cudaMemcpyAsync(d_ids, pixel_ids, (size_t)pixel_count * 4, cudaMemcpyHostToDevice, st));
+        sc->stats.h2d_bytes += (uint64_t)pixel_count * 4;
+    }
+    CKR(cudaMemsetAsync(p.totals, 0, sizeof(WaveTotals), st));
+    CKR(cudaMemsetAsync(p.tcount, 0, sizeof(TraceCounters), st));
+    CKR(cudaEventRecord(sc->ev0, st));
+
+    for (uint32_t p0 = 0; p0 < pixel_count; p0 += pix_per_batch) {
+        const uint32_t npix = std::min(pix_per_batch, pixel_count - p0);
+        for (uint32_t s0 = 0; s0 < sample_count; s0 += spp_chunk) {
+            const uint32_t ns = std::min(spp_chunk, sample_count - s0);
+            const uint32_t n_slots = npix * ns;
+            k_raygen<<<cdiv(n_slots, 256), 256, 0, st>>>(dcam, prm, p.paths, p.q[0], n_slots, ns, width, d_ids, pixel_begin, p0,
+                                                        sample_begin + s0, 0.5f, p.counts);
+            { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_raygen failed: %s", cudaGetErrorString(e_))); }
+            launches++;
+            rc = run_waves(sc, prm, n_slots, flags, &launches);
+            if (rc) return done(rc);
+            k_resolve<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, p0);
+            { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_resolve failed: %s", cudaGetErrorString(e_))); }
+            launches++;
+        }
+    }
+    k_finalize<<<cdiv(pixel_count, 128), 128, 0, st>>>(accum, pixel_count, sample_count, nullptr, flags & 3u, (float4 *)out_dev, d_ids, pixel_begin);
+    { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_finalize failed: %s", cudaGetErrorString(e_))); }
+    launches++;
+    CKR(cudaEventRecord(sc->ev1, st));
+    TraceCounters tc;
+    CKR(cudaMemcpyAsync(&tc, p.tcount, sizeof(tc), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    float ms = 0;
+    CKR(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    sc->stats.gpu_ms = ms;
+    sc->stats.kernel_launches = launches;
+    if (out_counters) {
+        out_counters->ray_count = sc->stats.closest_rays + sc->stats.shadow_rays;
+        out_counters->sphere_check_count = tc.sphere_checks;
+        out_counters->mesh_check_count = tc.cluster_checks;
+    }
+    if (user_stream) {      // make the caller's stream see the result
+        CKR(cudaEventRecord(sc->ev1, st));
+        CKR(cudaStreamWaitEvent(user_stream, sc->ev1, 0));
+    }
+    return done(RT_OK);
+#undef CKR
+}
+
+extern "C" int rt_render_device(rt_scene *scene, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height,
+                                const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count, uint32_t sample_begin,
+                                uint32_t sample_count, uint32_t flags, float *out_rgba_device, void *stream, rt_counters *out_counters) {
+    g_err.clear();
+    return render_impl(scene, cam, params, width, height, pixel_ids, pixel_begin, pixel_count, sample_begin, sample_count, flags,
+                       out_rgba_device, (cudaStream_t)stream, out_counters);
+}
+
+extern "C" int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height,
+                         const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count, uint32_t sample_begin,
+                         uint32_t sample_count, uint32_t flags, float *out_rgba_host, rt_counters *out_counters) {
+    g_err.clear();
+    if (!scene || !out_rgba_host) return fail(RT_ERR_ARG, "null argument");
+    if (flags & RT_OUT_FULLFRAME) return fail(RT_ERR_ARG, "RT_OUT_FULLFRAME is a device-output mode");
+    CK(cudaSetDevice(scene->device));
+    float *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_out, std::max<size_t>(1, (size_t)pixel_count) * 16));
+    int rc = render_impl(scene, cam, params, width, height, pixel_ids, pixel_begin, pixel_count, sample_begin, sample_count, flags,
+                         d_out, nullptr, out_counters);
+    if (rc == RT_OK && pixel_count) {
+        cudaError_t e = cudaMemcpyAsync(out_rgba_host, d_out, (size_t)pixel_count * 16, cudaMemcpyDeviceToHost, scene->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(scene->stream);
+        if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "framebuffer download failed: %s", cudaGetErrorString(e));
+        scene->stats.d2h_bytes += (uint64_t)pixel_count * 16;
+    }
+    cudaFree(d_out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rt_trace_rays / rt_trace_primary / rt_trace_color
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray *rays, uint64_t n, int any_hit, rt_hit *out_hits,
+                             rt_counters *out_counters) {
+    g_err.clear();
+    if (!sc || !params || (n && (!rays || !out_hits))) return fail(RT_ERR_ARG, "null argument");
+    CK(cudaSetDevice(sc->device));
+    cudaStream_t st = sc->stream;
+    memset(&sc->stats, 0, sizeof(sc->stats));
+    unsigned long long tot_s = 0, tot_c = 0;
+    const uint32_t chunk = 1u << 20;
+    DevArena tmp;
+    auto done = [&](int r) { tmp.release(); return r; };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    float *d_rays; RayQueue q; HitRec *hits; ApiHit *api; TraceCounters *tc;
+    uint32_t cap = (uint32_t)std::min<uint64_t>(n ? n : 1, chunk);
+    CKR(tmp.alloc(&d_rays, 6 * (size_t)cap)); CKR(tmp.alloc(&q.o, cap)); CKR(tmp.alloc(&q.d, cap)); CKR(tmp.alloc(&hits, cap));
+    CKR(tmp.alloc(&api, cap)); CKR(tmp.alloc(&tc, 1));
+    CKR(cudaMemsetAsync(tc, 0, sizeof(TraceCounters), st));
+    CKR(cudaEventRecord(sc->ev0, st));
+    for (uint64_t b = 0; b < n; b += chunk) {
+        uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - b);
+        CKR(cudaMemcpyAsync(d_rays, rays + b, (size_t)m * sizeof(rt_ray), cudaMemcpyHostToDevice, st));
+        k_upload_rays<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q);
+        uint32_t grid = std::min(cdiv(m, 128), (uint32_t)sc->sm_count * 16u);
+        if (any_hit == RT_TRACE_ANY) k_trace_any<<<grid, 128, 0, st>>>(sc->d, params->ray_bias, q, m, hits);
+        else if (any_hit == RT_TRACE_BRUTE) k_trace_brute<<<cdiv(m, 128), 128, 0, st>>>(sc->d, params->ray_bias, q, m, hits);
+        else k_trace_closest<true><<<grid, 128, 0, st>>>(sc->d, params->ray_bias, q, nullptr, m, hits, tc);
+        k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, params->ray_bias, q, hits, m, api);
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "trace launch failed: %s", cudaGetErrorString(e_))); }
+        CKR(cudaMemcpyAsync(out_hits + b, api, (size_t)m * sizeof(ApiHit), cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        sc->stats.kernel_launches += 3;
+        sc->stats.closest_rays += m;
+    }
+    CKR(cudaEventRecord(sc->ev1, st));
+    TraceCounters htc;
+    CKR(cudaMemcpyAsync(&htc, tc, sizeof(htc), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    float ms = 0; CKR(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    sc->stats.gpu_ms = ms;
+    tot_s = htc.sphere_checks; tot_c = htc.cluster_checks;
+    if (out_counters) { out_counters->ray_count = n; out_counters->sphere_check_count = tot_s; out_counters->mesh_check_count = tot_c; }
+    return done(RT_OK);
+#undef CKR
+}
+
+extern "C" int rt_trace_primary(rt_scene *sc, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height,
+                                const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count, uint32_t sample_begin,
+                                uint32_t sample_count, rt_ray *out_rays, rt_hit *out_hits) {
+    g_err.clear();
+    if (!sc || !cam) return fail(RT_ERR_ARG, "null argument");
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (!width || !height) return fail(RT_ERR_ARG, "empty frame");
+    const uint64_t frame = (uint64_t)width * height;
+    if (!pixel_ids && (uint64_t)pixel_begin + pixel_count > frame) return fail(RT_ERR_ARG, "pixel range exceeds the frame");
+    if (pixel_ids) for (uint32_t k = 0; k < pixel_count; ++k) if (pixel_ids[k] >= frame) return fail(RT_ERR_ARG, "pixel id %u out of range", pixel_ids[k]);
+    if (!pixel_count || !sample_count) return RT_OK;
+    CK(cudaSetDevice(sc->device));
+    cudaStream_t st = sc->stream;
+    memset(&sc->stats, 0, sizeof(sc->stats));
+    const uint32_t limit = 1u << 20;
+    const uint32_t spp_chunk = std::min(sample_count, limit);
+    const uint32_t pix_per_batch = std::max(1u, std::min(pixel_count, limit / spp_chunk));
+    rc = ensure_pool(sc, pix_per_batch * spp_chunk, params->bounce_depth);
+    if (rc) return rc;
+    Pool &p = sc->pool;
+    DevParams prm = to_dev_params(params);
+    DevCamera dcam = to_dev_camera(cam);
+    DevArena tmp;
+    auto done = [&](int r) { tmp.release(); return r; };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    uint32_t *d_ids = nullptr; float *d_rays; ApiHit *api;
+    const uint32_t cap = pix_per_batch * spp_chunk;
+    CKR(tmp.alloc(&d_rays, 6 * (size_t)cap)); CKR(tmp.alloc(&api, cap));
+    if (pixel_ids) { CKR(tmp.alloc(&d_ids, pixel_count)); CKR(cudaMemcpyAsync(d_ids, pixel_ids, (size_t)pixel_count * 4, cudaMemcpyHostToDevice, st)); }
+    CKR(cudaEventRecord(sc->ev0, st));
+    for (uint32_t p0 = 0; p0 < pixel_count; p0 += pix_per_batch) {
+        const uint32_t npix = std::min(pix_per_batch, pixel_count - p0);
+        for (uint32_t s0 = 0; s0 < sample_count; s0 += spp_chunk) {
+            const uint32_t ns = std::min(spp_chunk, sample_count - s0);
+            const uint32_t m = npix * ns;
+            k_raygen<<<cdiv(m, 256), 256, 0, st>>>(dcam, prm, p.paths, p.q[0], m, ns, width, d_ids, pixel_begin, p0, sample_begin + s0, 0.5f, p.counts);
+            if (out_hits) {
+                uint32_t grid = std::min(cdiv(m, 128), (uint32_t)sc->sm_count * 16u);
+                k_trace_closest<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[0], nullptr, m, p.hits, p.tcount);
+                k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, prm.ray_bias, p.q[0], p.hits, m, api);
+                sc->stats.kernel_launches += 2; sc->stats.closest_rays += m;
+            }
+            if (out_rays) k_queue_to_rays<<<cdiv(m, 256), 256, 0, st>>>(p.q[0], m, d_rays);
+            { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "primary launch failed: %s", cudaGetErrorString(e_))); }
+            sc->stats.kernel_launches += 1;
+            // entries are pixel-major over the WHOLE call: (p0 + k) * sample_count + s0 + s
+            for (uint32_t k = 0; k < npix; ++k) {
+                size_t dst = (size_t)(p0 + k) * sample_count + s0, src = (size_t)k * ns;
+                if (out_hits) CKR(cudaMemcpyAsync(out_hits + dst, api + src, (size_t)ns * sizeof(ApiHit), cudaMemcpyDeviceToHost, st));
+                if (out_rays) CKR(cudaMemcpyAsync(out_rays + dst, d_rays + 6 * src, (size_t)ns * sizeof(rt_ray), cudaMemcpyDeviceToHost, st));
+                if (ns == sample_count) {   // contiguous: one copy covers the whole batch
+                    if (out_hits) CKR(cudaMemcpyAsync(out_hits + dst, api + src, (size_t)ns * npix * sizeof(ApiHit), cudaMemcpyDeviceToHost, st));
+                    if (out_rays) CKR(cudaMemcpyAsync(out_rays + dst, d_rays + 6 * src, (size_t)ns * npix * sizeof(rt_ray), cudaMemcpyDeviceToHost, st));
+                    break;
+                }
+            }
+            CKR(cudaStreamSynchronize(st));
+        }
+    }
+    CKR(cudaEventRecord(sc->ev1, st));
+    CKR(cudaStreamSynchronize(st));
+    float ms = 0; CKR(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    sc->stats.gpu_ms = ms;
+    return done(RT_OK);
+#undef CKR
+}
+
+extern "C" int rt_trace_color(rt_scene *sc, const rt_params *params, const rt_ray *rays, const uint64_t *seeds, uint64_t n,
+                              float *out_rgba, rt_counters *out_counters) {
+    g_err.clear();
+    if (!sc || (n && (!rays || !seeds || !out_rgba))) return fail(RT_ERR_ARG, "null argument");
+    int rc = check_params(params);
+    if (rc) return rc;
+    CK(cudaSetDevice(sc->device));
+    cudaStream_t st = sc->stream;
+    memset(&sc->stats, 0, sizeof(sc->stats));
+    if (out_counters) memset(out_counters, 0, sizeof(*out_counters));
+    if (!n) return RT_OK;
+    rc = ensure_spec_table(sc, params->spec_samples);
+    if (rc) return rc;
+    const uint32_t chunk = (uint32_t)std::min<uint64_t>(n, 1u << 20);
+    rc = ensure_pool(sc, chunk, params->bounce_depth);
+    if (rc) return rc;
+    Pool &p = sc->pool;
+    DevParams prm = to_dev_params(params);
+    DevArena tmp;
+    auto done = [&](int r) { tmp.release(); return r; };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    float *d_rays; uint64_t *d_seeds;
+    CKR(tmp.alloc(&d_rays, 6 * (size_t)chunk)); CKR(tmp.alloc(&d_seeds, chunk));
+    CKR(cudaMemsetAsync(p.tcount, 0, sizeof(TraceCounters), st));
+    uint64_t launches = 0;
+    CKR(cudaEventRecord(sc->ev0, st));
+    for (uint64_t b = 0; b < n; b += chunk) {
+        uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - b);
+        CKR(cudaMemcpyAsync(d_rays, rays + b, (size_t)m * sizeof(rt_ray), cudaMemcpyHostToDevice, st));
+        CKR(cudaMemcpyAsync(d_seeds, seeds + b, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        k_paths_from_rays<<<cdiv(m, 256), 256, 0, st>>>(prm, p.paths, p.q[0], m, d_rays, d_seeds, p.counts);
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_paths_from_rays failed: %s", cudaGetErrorString(e_))); }
+        launches++;
+        rc = run_waves(sc, prm, m, RT_FLAG_COUNTERS, &launches);
+        if (rc) return done(rc);
+        CKR(cudaMemcpyAsync(out_rgba + 4 * b, p.paths.acc, (size_t)m * 16, cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+    }
+    CKR(cudaEventRecord(sc->ev1, st));
+    TraceCounters tc;
+    CKR(cudaMemcpyAsync(&tc, p.tcount, sizeof(tc), cudaMemcpyDeviceToHost, st));
+    CKR(cudaStreamSynchronize(st));
+    float ms = 0; CKR(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
+    sc->stats.gpu_ms = ms; sc->stats.kernel_launches = launches;
+    if (out_counters) {
+        out_counters->ray_count = sc->stats.closest_rays + sc->stats.shadow_rays;
+        out_counters->sphere_check_count = tc.sphere_checks; out_counters->mesh_check_count = tc.cluster_checks;
+    }
+    return done(RT_OK);
+#undef CKR
+}
+
+extern "C" int rt_get_stats(const rt_scene *sc, rt_stats *out) {
+    if (!sc || !out) return fail(RT_ERR_ARG, "null argument");
+    *out = sc->stats;
+    return RT_OK;
+}
+
+extern "C" int rt_get_hierarchy_info(const rt_scene *sc, uint64_t out[8]) {
+    if (!sc || !out) return fail(RT_ERR_ARG, "null argument");
+    memcpy(out, sc->info, sizeof(sc->info));
+    return RT_OK;
+}
+
+extern "C" int rt_rng_kat(int device, uint64_t seed, uint32_t n, uint64_t *out_host) {
+    g_err.clear();
+    if (!out_host) return fail(RT_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    uint64_t *d;
+    CK(cudaMalloc((void **)&d, std::max(1u, n) * 8));
+    k_rng_kat<<<1, 1>>>(seed, n, d);
+    cudaError_t e = cudaMemcpy(out_host, d, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "rng kat failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}

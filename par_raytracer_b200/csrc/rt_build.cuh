@@ -1,0 +1,409 @@
+// rt_build.cuh -- GPU construction of the bounding-sphere cluster hierarchy (kernel group K2).
+//
+// The reference builds its hierarchy on the host by greedy agglomeration: repeatedly merge the pair
+// of spheres whose enclosing sphere has the smallest radius (bsphere.cpp:281-314, 399-428; O(n^3),
+// leaves = whole mesh groups). This file is the B200 form of the same idea at triangle granularity:
+//   1. per-triangle minimal enclosing spheres + 63-bit Morton keys of their centres,
+//   2. a bitonic sort of (key, triangle) pairs,
+//   3. PLOC-style parallel agglomeration: every cluster looks +-PLOC_RADIUS neighbours along the Morton
+//      order for the partner with the smallest enclosing-sphere radius (the reference's heuristic,
+//      bsphere.cpp:295-299); mutual choices merge; survivors are compacted with a prefix sum,
+//   4. subtrees of <= RT_LEAF_MAX triangles collapse into clusters; nodes are laid out in depth-first
+//      pre-order (every subtree contiguous in memory) with both child spheres stored in the parent,
+//   5. triangles are gathered into cluster order as SoA float4 records.
+// Nothing here is bit-compared with the reference: any conservative hierarchy yields the same hits.
+#pragma once
+#include "rt_common.cuh"
+
+#ifndef RT_LEAF_MAX
+#define RT_LEAF_MAX 4
+#endif
+#define PLOC_RADIUS 16
+
+// ---- small utilities -----------------------------------------------------------------------
+
+RT_DEVICE uint32_t float_flip(float f) {        // order-preserving float -> uint
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+RT_DEVICE float float_unflip(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+RT_DEVICE uint64_t expand21(uint32_t v) {       // spread 21 bits to every third bit
+    uint64_t x = v & 0x1FFFFFu;
+    x = (x | x << 32) & 0x1F00000000FFFFULL;
+    x = (x | x << 16) & 0x1F0000FF0000FFULL;
+    x = (x | x << 8) & 0x100F00F00F00F00FULL;
+    x = (x | x << 4) & 0x10C30C30C30C30C3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+
+// Smallest sphere around two spheres (cf. BoundingSphere_FromChildren, bsphere.cpp:248-279), padded so
+// that float rounding can never make it miss a child.
+RT_DEVICE float4 enclose_spheres(float4 a, float4 b) {
+    float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+    float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (d + b.w <= a.w) return a;
+    if (d + a.w <= b.w) return b;
+    float r = 0.5f * (d + a.w + b.w);
+    float k = d > 0.0f ? (r - a.w) / d : 0.0f;
+    float4 o = make_float4(a.x + dx * k, a.y + dy * k, a.z + dz * k, 0.0f);
+    // radius = exact worst case from the rounded centre
+    float ex = o.x - a.x, ey = o.y - a.y, ez = o.z - a.z;
+    float fx = o.x - b.x, fy = o.y - b.y, fz = o.z - b.z;
+    float ra = sqrtf(ex * ex + ey * ey + ez * ez) + a.w;
+    float rb = sqrtf(fx * fx + fy * fy + fz * fz) + b.w;
+    o.w = fmaxf(ra, rb) * 1.000002f + 1e-30f;
+    return o;
+}
+RT_DEVICE float enclose_radius(float4 a, float4 b) {
+    float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+    float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (d + b.w <= a.w) return a.w;
+    if (d + a.w <= b.w) return b.w;
+    return 0.5f * (d + a.w + b.w);
+}
+
+// ---- 1. per-triangle setup -------------------------------------------------------------------
+
+struct BuildInput {
+    const float *positions;
+    const uint32_t *idx_positions;     // concatenated group index buffers
+    const uint32_t *group_first;       // n_groups + 1 (index units)
+    uint32_t n_groups;
+    uint32_t n_tris;
+};
+
+RT_DEVICE f3 ld3(const float *p, uint32_t i) { return mk3(p[3 * (size_t)i], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]); }
+
+__global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, uint32_t *bounds /*6 flipped floats*/) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    f3 lo = mk3(FLT_MAX, FLT_MAX, FLT_MAX), hi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    if (j < in.n_tris) {
+        f3 a = ld3(in.positions, in.idx_positions[3 * (size_t)j + 0]);
+        f3 b = ld3(in.positions, in.idx_positions[3 * (size_t)j + 1]);
+        f3 c = ld3(in.positions, in.idx_positions[3 * (size_t)j + 2]);
+        // minimal enclosing sphere: midpoint of the longest edge if the opposite vertex is inside, else circumsphere
+        f3 ab = b - a, ac = c - a, bc = c - b;
+        float lab = dot3(ab, ab), lac = dot3(ac, ac), lbc = dot3(bc, bc);
+        f3 p0 = a, p1 = b, p2 = c; float l = lab;
+        if (lac > l) { p0 = a; p1 = c; p2 = b; l = lac; }
+        if (lbc > l) { p0 = b; p1 = c; p2 = a; l = lbc; }
+        f3 ctr = (p0 + p1) * 0.5f;
+        f3 dv = p2 - ctr;
+        if (dot3(dv, dv) > 0.25f * l) {
+            // acute: circumcentre = a + (|ac|^2 (n x ab) + |ab|^2 (ac x n)) / (2 |n|^2), n = ab x ac
+            f3 n = cross3(ab, ac);
+            float n2 = dot3(n, n);
+            if (n2 > 0.0f) {
+                f3 t = cross3(n, ab) * lac + cross3(ac, n) * lab;
+                ctr = a + t * (0.5f / n2);
+            }
+        }
+        f3 da = a - ctr, db = b - ctr, dc = c - ctr;
+        float r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc)));
+        if (!(r2 < FLT_MAX)) { ctr = (a + b + c) * (1.0f / 3.0f); da = a - ctr; db = b - ctr; dc = c - ctr;
+                                r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc))); }
+        tri_sphere[j] = make_float4(ctr.x, ctr.y, ctr.z, sqrtf(r2) * 1.000002f + 1e-30f);
+        lo = ctr; hi = ctr;
+    }
+    // block reduce of centre bounds
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o)); hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bounds[0], float_flip(lo.x)); atomicMin(&bounds[1], float_flip(lo.y)); atomicMin(&bounds[2], float_flip(lo.z));
+        atomicMax(&bounds[3], float_flip(hi.x)); atomicMax(&bounds[4], float_flip(hi.y)); atomicMax(&bounds[5], float_flip(hi.z));
+    }
+}
+
+__global__ void k_morton(uint32_t n, uint32_t n_pad, const float4 *tri_sphere, const uint32_t *bounds, uint64_t *keys, uint32_t *vals) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    if (j >= n) { keys[j] = ~0ULL; vals[j] = ~0u; return; }
+    float lox = float_unflip(bounds[0]), loy = float_unflip(bounds[1]), loz = float_unflip(bounds[2]);
+    float hix = float_unflip(bounds[3]), hiy = float_unflip(bounds[4]), hiz = float_unflip(bounds[5]);
+    float ext = fmaxf(hix - lox, fmaxf(hiy - loy, hiz - loz));
+    float s = ext > 0.0f ? 2097151.0f / ext : 0.0f;
+    float4 c = tri_sphere[j];
+    uint32_t qx = (uint32_t)fminf(fmaxf((c.x - lox) * s, 0.0f), 2097151.0f);
+    uint32_t qy = (uint32_t)fminf(fmaxf((c.y - loy) * s, 0.0f), 2097151.0f);
+    uint32_t qz = (uint32_t)fminf(fmaxf((c.z - loz) * s, 0.0f), 2097151.0f);
+    keys[j] = (expand21(qx) << 2) | (expand21(qy) << 1) | expand21(qz);
+    vals[j] = j;
+}
+
+// ---- 2. bitonic sort of (key, val), lexicographic so the order is total and deterministic --------
+
+RT_DEVICE bool kv_greater(uint64_t ka, uint32_t va, uint64_t kb, uint32_t vb) { return ka > kb || (ka == kb && va > vb); }
+
+__global__ void k_bitonic_global(uint64_t *keys, uint32_t *vals, uint32_t n_pad, uint32_t j, uint32_t k) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    uint32_t l = i ^ j;
+    if (l > i) {
+        uint64_t ka = keys[i], kb = keys[l];
+        uint32_t va = vals[i], vb = vals[l];
+        bool up = (i & k) == 0;
+        if (kv_greater(ka, va, kb, vb) == up) { keys[i] = kb; keys[l] = ka; vals[i] = vb; vals[l] = va; }
+    }
+}
+
+#define BITONIC_TILE 2048
+// all (k, j) steps with j < BITONIC_TILE for k in [k_begin, k_end] (powers of two), inside shared memory
+__global__ void __launch_bounds__(1024) k_bitonic_shared(uint64_t *keys, uint32_t *vals, uint32_t k_begin, uint32_t k_end, int only_tail) {
+    __shared__ uint64_t sk[BITONIC_TILE];
+    __shared__ uint32_t sv[BITONIC_TILE];
+    uint32_t base = blockIdx.x * BITONIC_TILE;
+    for (uint32_t t = threadIdx.x; t < BITONIC_TILE; t += blockDim.x) { sk[t] = keys[base + t]; sv[t] = vals[base + t]; }
+    __syncthreads();
+    for (uint32_t k = k_begin; k <= k_end; k <<= 1) {
+        uint32_t j0 = only_tail ? (BITONIC_TILE >> 1) : (k >> 1);
+        if (j0 > (BITONIC_TILE >> 1)) j0 = BITONIC_TILE >> 1;
+        for (uint32_t j = j0; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < BITONIC_TILE; t += blockDim.x) {
+                uint32_t l = t ^ j;
+                if (l > t) {
+                    bool up = ((base + t) & k) == 0;
+                    if (kv_greater(sk[t], sv[t], sk[l], sv[l]) == up) {
+                        uint64_t tk = sk[t]; sk[t] = sk[l]; sk[l] = tk;
+                        uint32_t tv = sv[t]; sv[t] = sv[l]; sv[l] = tv;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t t = threadIdx.x; t < BITONIC_TILE; t += blockDim.x) { keys[base + t] = sk[t]; vals[base + t] = sv[t]; }
+}
+
+// ---- prefix sum over packed (valid, merge) counters ----------------------------------------------
+
+#define SCAN_BLOCK 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_reduce(const uint64_t *in, uint32_t n, uint64_t *block_sums) {
+    __shared__ uint64_t sh[SCAN_BLOCK / 32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t s = 0;
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) s += in[base + k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint64_t t = 0; for (int w = 0; w < SCAN_BLOCK / 32; ++w) t += sh[w]; block_sums[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_blocksums(uint64_t *block_sums, uint32_t nb, uint64_t *total) {
+    __shared__ uint64_t sh[1024];
+    __shared__ uint64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = i < nb ? block_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t o = 1; o < 1024; o <<= 1) {
+            uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint64_t incl = sh[threadIdx.x];
+        if (i < nb) block_sums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const uint64_t *in, uint32_t n, const uint64_t *block_sums, uint64_t *out) {
+    __shared__ uint64_t sh[SCAN_BLOCK];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS];
+    uint64_t s = 0;
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t o = 1; o < SCAN_BLOCK; o <<= 1) {
+        uint64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint64_t run = block_sums[blockIdx.x] + sh[threadIdx.x] - s;
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+
+// ---- 3. PLOC agglomeration --------------------------------------------------------------------------
+
+struct TempTree {           // 2n - 1 nodes: [0, n) = sorted triangles, [n, 2n-1) = merges in creation order
+    int32_t *c0, *c1, *parent;
+    uint32_t *size;          // triangles in subtree
+    uint32_t *kept;          // internal nodes with size > RT_LEAF_MAX in subtree (incl. self)
+    float4 *sphere;
+};
+
+__global__ void k_ploc_init(uint32_t n, const uint32_t *sorted_tri, const float4 *tri_sphere, float4 *cl_sphere, int32_t *cl_node,
+                            TempTree t) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 s = tri_sphere[sorted_tri[i]];
+    cl_sphere[i] = s; cl_node[i] = (int32_t)i;
+    t.c0[i] = -1; t.c1[i] = -1; t.parent[i] = -1; t.size[i] = 1; t.kept[i] = 0; t.sphere[i] = s;
+}
+
+__global__ void __launch_bounds__(256) k_ploc_nn(uint32_t m, const float4 *cl_sphere, uint32_t *nn, int pair_mode) {
+    __shared__ float4 sh[256 + 2 * PLOC_RADIUS];
+    int base = (int)(blockIdx.x * 256) - PLOC_RADIUS;
+    for (int t = threadIdx.x; t < 256 + 2 * PLOC_RADIUS; t += 256) {
+        int g = base + t;
+        sh[t] = (g >= 0 && g < (int)m) ? cl_sphere[g] : make_float4(0, 0, 0, -1.0f);
+    }
+    __syncthreads();
+    uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= m) return;
+    if (pair_mode) { uint32_t j = i ^ 1u; nn[i] = j < m ? j : i; return; }
+    float4 me = sh[threadIdx.x + PLOC_RADIUS];
+    float best = FLT_MAX; uint32_t bj = i;
+    for (int o = -PLOC_RADIUS; o <= PLOC_RADIUS; ++o) {
+        if (o == 0) continue;
+        float4 other = sh[threadIdx.x + PLOC_RADIUS + o];
+        if (other.w < 0.0f) continue;
+        float r = enclose_radius(me, other);
+        if (r < best) { best = r; bj = (uint32_t)((int)i + o); }
+    }
+    nn[i] = bj;
+}
+
+// flags packed as (merge << 32) | valid.  A mutual pair (i, nn[i]) merges into the lower position.
+__global__ void k_ploc_flags(uint32_t m, const uint32_t *nn, uint64_t *flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t j = nn[i];
+    bool mutual = j != i && nn[j] == i;
+    uint64_t valid = (mutual && i > j) ? 0 : 1;
+    uint64_t merge = (mutual && i < j) ? 1 : 0;
+    flags[i] = (merge << 32) | valid;
+}
+
+__global__ void k_ploc_merge(uint32_t m, uint32_t n, uint32_t nodes_created, const uint32_t *nn, const uint64_t *flags, const uint64_t *scan,
+                             const float4 *cl_sphere, const int32_t *cl_node, float4 *out_sphere, int32_t *out_node, TempTree t) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint64_t f = flags[i];
+    if ((f & 1ull) == 0) return;
+    uint64_t sc = scan[i];
+    uint32_t pos = (uint32_t)(sc & 0xffffffffull);
+    if (f >> 32) {
+        uint32_t j = nn[i];
+        int32_t a = cl_node[i], b = cl_node[j];
+        int32_t id = (int32_t)(n + nodes_created + (uint32_t)(sc >> 32));
+        float4 s = enclose_spheres(cl_sphere[i], cl_sphere[j]);
+        t.c0[id] = a; t.c1[id] = b; t.parent[id] = -1; t.parent[a] = id; t.parent[b] = id;
+        uint32_t sz = t.size[a] + t.size[b];
+        t.size[id] = sz;
+        t.kept[id] = sz > RT_LEAF_MAX ? 1u + t.kept[a] + t.kept[b] : 0u;
+        t.sphere[id] = s;
+        out_sphere[pos] = s; out_node[pos] = id;
+    } else {
+        out_sphere[pos] = cl_sphere[i]; out_node[pos] = cl_node[i];
+    }
+}
+
+// ---- 4. layout -------------------------------------------------------------------------------------
+
+// Per temp node: first triangle slot of its subtree in cluster order, pre-order index among kept nodes, depth.
+__global__ void k_layout(uint32_t n_nodes_total, TempTree t, uint32_t *tri_offset, uint32_t *kept_index, uint32_t *max_depth) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes_total) return;
+    uint32_t off = 0, idx = 0, depth = 0;
+    int32_t cur = (int32_t)v;
+    int32_t p = t.parent[cur];
+    while (p >= 0) {
+        bool right = t.c1[p] == cur;
+        if (right) { off += t.size[t.c0[p]]; idx += t.kept[t.c0[p]]; }
+        idx += 1;
+        depth++;
+        cur = p; p = t.parent[cur];
+    }
+    tri_offset[v] = off;
+    kept_index[v] = idx;
+    if (t.size[v] > RT_LEAF_MAX) atomicMax(max_depth, depth + 1);
+}
+
+__global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, const uint32_t *tri_offset, const uint32_t *kept_index,
+                             HNode *nodes) {
+    uint32_t v = n + blockIdx.x * blockDim.x + threadIdx.x;   // internal temp nodes only
+    if (v >= n_nodes_total) return;
+    if (t.size[v] <= RT_LEAF_MAX) return;
+    HNode o;
+    int32_t a = t.c0[v], b = t.c1[v];
+    o.s0 = t.sphere[a]; o.s1 = t.sphere[b];
+    o.c0 = t.size[a] > RT_LEAF_MAX ? (int32_t)kept_index[a] : leaf_ref(tri_offset[a], t.size[a]);
+    o.c1 = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
+    o.pad0 = t.size[v]; o.pad1 = 0;
+    nodes[kept_index[v]] = o;
+}
+
+// ---- 5. gather triangles into cluster order ----------------------------------------------------------
+
+struct GatherInput {
+    const float *positions, *texcoords, *normals, *tangents;
+    const uint32_t *idx_p, *idx_t, *idx_n;
+    const uint32_t *group_first;
+    const uint32_t *group_rank_base;    // rank of the group's first triangle in the reference's visit order
+    const int32_t *group_object;        // sphere index holding the group
+    const int32_t *group_material;      // resolved (default -> n_materials)
+    uint32_t n_groups, n_tris;
+};
+
+RT_DEVICE uint32_t find_group(const uint32_t *group_first, uint32_t n_groups, uint32_t index) {
+    uint32_t lo = 0, hi = n_groups;     // last g with group_first[g] <= index
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (group_first[mid] <= index) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void k_gather(GatherInput in, const uint32_t *sorted_tri, const uint32_t *tri_offset, TriRec *tris, uint32_t *tri_rank,
+                         float4 *tri_uv, float4 *tri_nrm, float4 *tri_tan, uint32_t *tri_vertex0, int32_t *tri_object) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // sorted position == temp leaf node id
+    if (i >= in.n_tris) return;
+    uint32_t j = sorted_tri[i];                               // input triangle
+    uint32_t dst = tri_offset[i];
+    uint32_t g = find_group(in.group_first, in.n_groups, 3u * j);
+    uint32_t v0 = 3u * j - in.group_first[g];
+    f3 a = ld3(in.positions, in.idx_p[3 * (size_t)j + 0]);
+    f3 b = ld3(in.positions, in.idx_p[3 * (size_t)j + 1]);
+    f3 c = ld3(in.positions, in.idx_p[3 * (size_t)j + 2]);
+    f3 ab = b - a;                                            // raytracer.cpp:85-86, 91 -- unfused, exact
+    f3 ac = c - a;
+    f3 n = cross3(ab, ac);
+    TriRec r;
+    r.r0 = make_float4(n.x, n.y, n.z, a.x);
+    r.r1 = make_float4(a.y, a.z, ab.x, ab.y);
+    r.r2 = make_float4(ab.z, ac.x, ac.y, ac.z);
+    tris[dst] = r;
+    tri_rank[dst] = in.group_rank_base[g] + v0 / 3u;
+    tri_vertex0[dst] = v0;
+    tri_object[dst] = in.group_object[g];
+    const float *t0 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 0];
+    const float *t1 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 1];
+    const float *t2 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 2];
+    tri_uv[2 * (size_t)dst + 0] = make_float4(t0[0], t0[1], t1[0], t1[1]);
+    tri_uv[2 * (size_t)dst + 1] = make_float4(t2[0], t2[1], __int_as_float(in.group_material[g]), 0.0f);
+    for (int k = 0; k < 3; ++k) {
+        uint32_t ni = in.idx_n[3 * (size_t)j + k];
+        f3 nn = ld3(in.normals, ni);
+        tri_nrm[3 * (size_t)dst + k] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+        if (tri_tan) {
+            f3 tt = ld3(in.tangents, ni);
+            tri_tan[3 * (size_t)dst + k] = make_float4(tt.x, tt.y, tt.z, 0.0f);
+        }
+    }
+}

@@ -1,0 +1,118 @@
+// rt_common.cuh -- device-side math and data layout shared by every kernel of librt_b200.so.
+//
+// Arithmetic contract: everything that decides a hit, a ray or a branch uses IEEE
+// binary32 +,-,*,/ and sqrt in the reference's operation ORDER with no FMA contraction. The whole
+// translation unit is compiled with -fmad=false (and the default -prec-div=true -prec-sqrt=true
+// -ftz=false); code that is allowed to be approximate (bounding-sphere culling) uses explicit
+// __fmaf_rn / approx intrinsics and says so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+#define RT_DEVICE __device__ __forceinline__
+
+struct f3 { float x, y, z; };
+
+RT_DEVICE f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_DEVICE f3 mk3(float4 v) { return mk3(v.x, v.y, v.z); }
+// mathlib.h:199-232
+RT_DEVICE f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DEVICE f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DEVICE f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_DEVICE f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_DEVICE f3 neg3(f3 a) { return a * -1.0f; }                                    // mathlib.h:229-232
+RT_DEVICE float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // mathlib.h:234-237
+RT_DEVICE f3 cross3(f3 a, f3 b) {                                                // mathlib.h:239-246
+    return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+RT_DEVICE f3 normalize3(f3 a) {                                                  // mathlib.h:253-262
+    float l2 = dot3(a, a);
+    if (l2 == 0.0f) return a;
+    float l = sqrtf(l2);
+    return mk3(a.x / l, a.y / l, a.z / l);
+}
+RT_DEVICE float max0(float x) { return 0.0f > x ? 0.0f : x; }                    // Max(0.0f, x), mathlib.h:8
+RT_DEVICE float clampf(float n, float a, float b) {                              // Clamp, mathlib.h:9
+    float m = n > a ? n : a;
+    return m < b ? m : b;
+}
+
+RT_DEVICE float4 mk4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+RT_DEVICE float4 mk4u(f3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __uint_as_float(w)); }
+
+// ---------------------------------------------------------------------------------------------
+// device-resident scene
+// ---------------------------------------------------------------------------------------------
+
+// One node of the GPU-built bounding-sphere hierarchy: the spheres of BOTH children live in the
+// parent (one 48-byte fetch decides both descents). child >= 0: node index; child < 0: cluster
+// (leaf) encoded as -(1 + first_triangle * 8 + triangle_count), triangle_count <= 7.
+struct __align__(16) HNode {
+    float4 s0;          // child 0: center.xyz, radius
+    float4 s1;          // child 1
+    int32_t c0, c1;
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(HNode) == 48, "HNode");
+
+RT_DEVICE int leaf_ref(uint32_t first, uint32_t count) { return -(int)(1u + first * 8u + count); }
+RT_DEVICE uint32_t leaf_first(int ref) { return ((uint32_t)(-ref) - 1u) >> 3; }
+RT_DEVICE uint32_t leaf_count(int ref) { return ((uint32_t)(-ref) - 1u) & 7u; }
+
+// Triangle record for the intersection test, in cluster order: exactly the intermediates the
+// reference computes first (raytracer.cpp:85-91), produced with the same unfused arithmetic:
+//   r0 = (n.x, n.y, n.z, a.x)  r1 = (a.y, a.z, ab.x, ab.y)  r2 = (ab.z, ac.x, ac.y, ac.z)
+// with ab = b - a, ac = c - a, n = Cross(ab, ac).
+struct __align__(16) TriRec { float4 r0, r1, r2; };
+
+struct DevMaterial {          // 64 B
+    float specular_intensity, index_of_refraction, alpha;
+    int32_t tex_ambient;
+    float ambient[3];  int32_t tex_diffuse;
+    float diffuse[3];  int32_t tex_specular;
+    float specular[3]; int32_t tex_alpha;
+    int32_t tex_bump; int32_t pad[3];
+};
+static_assert(sizeof(DevMaterial) == 80, "DevMaterial");
+
+struct DevTexture { uint32_t size_x, size_y, channels, offset; };
+
+struct DevLight {             // scene.h:9-15
+    int32_t type;
+    float color[3];
+    float position[3];
+    float facing[3];
+    float falloff;
+    float pad;
+};
+
+struct DevScene {
+    const HNode *nodes;
+    const TriRec *tris;
+    const uint32_t *tri_rank;      // tie-break rank: position in the reference's leaf visit order
+    const float4 *tri_uv;          // 2 per triangle: (u0 v0 u1 v1) (u2 v2 material_bits -)
+    const float4 *tri_nrm;         // 3 per triangle: vertex normals
+    const float4 *tri_tan;         // 3 per triangle: vertex tangents (NULL when no bump map)
+    const uint32_t *tri_vertex0;   // RaycastHit::vertex0 (raytracer.cpp:147)
+    const int32_t *tri_object;     // RaycastHit::object as sphere index (raytracer.cpp:148)
+    const DevMaterial *materials;  // [n_materials] + default at index n_materials
+    const DevTexture *textures;
+    const uint8_t *texels;
+    const DevLight *lights;
+    const float *srgb_lut;         // 256 entries: Color_SRGBToLinear(i / 255) computed by the host libm
+    const float4 *hamm_dir;        // 1024 tangent-space cosine-hemisphere directions (raytracer.cpp:322-328)
+    const float4 *spec_dir;        // [(n_materials + 1) * spec_samples] Phong-lobe directions (raytracer.cpp:290-300)
+    uint32_t n_tris, n_nodes, n_materials, n_lights;
+    int32_t root;                  // 0, or a leaf ref when the scene has <= one cluster
+};
+
+struct DevParams {
+    float ray_bias;
+    uint32_t reflection_samples, spec_samples, bounce_depth;
+    float bg[3];
+    uint32_t pad;
+    uint64_t base_seed;
+};
+
+#define RT_SEED_MULT 0x9E3779B97F4A7C15ULL

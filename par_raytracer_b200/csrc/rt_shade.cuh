@@ -1,0 +1,438 @@
+// rt_shade.cuh -- kernel groups K1 (ray generation), K4/K5 (shading, texture sampling, bounce generation),
+// K6 (stream compaction between stages) and K7 (accumulate / resolve).
+//
+// TraceRayColor (raytracer.cpp:413-577) is a recursion TREE whose nodes draw from ONE sequential random
+// stream in depth-first order, and how many draws a subtree takes depends on what its rays hit. To keep
+// every draw of every (pixel, sample) identical to the reference's, each sample is run as a coroutine
+// that executes the reference's recursion in the reference's order and yields at every TraceRay call:
+//
+//   wave w:   k_trace_closest  : all pending nodes' rays (one per live sample)        -> HitRec stream
+//             k_logic          : per live sample: consume the hit, shade, queue the shadow rays of the
+//                                node (they take no random numbers, so they ride in the same wave), then
+//                                walk the recursion forward -- draw, Russian-roulette, pick the next child
+//                                in DFS order -- until the next ray that really has to be traced; that ray
+//                                is appended (warp-aggregated atomics) to the next wave's compacted queue
+//             k_trace_shadow   : occlusion of the queued shadow rays, adds the pre-weighted radiance
+//
+// Radiance flows forward as a throughput T (component-wise products of the reference's own factors:
+// alpha, diffuse_color * w_diffuse * max(0, N.dir), specular_color * max(0, dir.-V), 1 - alpha), which is the
+// reference's nested sum re-associated; everything that steers control flow is bit-identical.
+#pragma once
+#include "rt_common.cuh"
+#include "rt_rng.cuh"
+#include "rt_trace.cuh"
+
+#define RT_FRAME_F4 6            // float4 words per recursion frame
+
+struct PathPool {
+    uint64_t *rng_cur, *rng_x, *rng_seed;
+    uint32_t *rng_n;
+    float4 *acc;                 // xyz: radiance gathered by the sample so far
+    float4 *node_T;              // xyz: throughput of the in-flight node, w: iters (int bits)
+    uint32_t *sp;                // live recursion frames
+    float4 *frames;              // [(level * RT_FRAME_F4 + k) * capacity + slot]
+    uint32_t capacity;
+};
+
+RT_DEVICE void rng_load(const PathPool &P, uint32_t s, PathRng &r) { r.cur = P.rng_cur[s]; r.x = P.rng_x[s]; r.seed = P.rng_seed[s]; r.n = P.rng_n[s]; }
+RT_DEVICE void rng_store(const PathPool &P, uint32_t s, const PathRng &r) { P.rng_cur[s] = r.cur; P.rng_x[s] = r.x; P.rng_n[s] = r.n; }
+
+// One atomicAdd per warp; every lane of the warp must call it.
+RT_DEVICE uint32_t warp_push(uint32_t *counter, bool pred) {
+    uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    uint32_t lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == 0 && mask) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// ---- main.cpp:164-177 MakeCameraRay ------------------------------------------------------------------
+struct DevCamera { float tan_a2, aspect, inv_width, inv_height; float pos[3], fwd[3], right[3], up[3]; };
+
+RT_DEVICE void camera_ray(const DevCamera &cam, float ox, float oy, f3 &org, f3 &dir) {
+    float nx = 2.0f * (ox + 0.5f) * cam.inv_width - 1.0f;
+    float ny = 1.0f - 2.0f * (oy + 0.5f) * cam.inv_height;
+    f3 fwd = mk3(cam.fwd[0], cam.fwd[1], cam.fwd[2]);
+    f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
+    f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
+    f3 a = ((right * cam.tan_a2) * cam.aspect) * nx;
+    f3 b = (up * cam.tan_a2) * ny;
+    dir = normalize3((fwd + a) + b);
+    org = mk3(cam.pos[0], cam.pos[1], cam.pos[2]);
+}
+
+// ---- K1: ray generation = RenderPixel's per-sample prologue (main.cpp:237-241 / 246-250) ---------------
+// slot s of the batch <-> (pixel_local = s / spp, sample = sample_begin + s % spp)
+__global__ void k_raygen(DevCamera cam, DevParams prm, PathPool P, RayQueue q, uint32_t n_slots, uint32_t spp, uint32_t width,
+                         const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_local0, uint32_t sample_begin,
+                         float jitter_scale, uint32_t *n_rays_out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    uint32_t pl = pixel_local0 + s / spp;
+    uint32_t samp = sample_begin + s % spp;
+    uint32_t pixel = pixel_ids ? pixel_ids[pl] : pixel_begin + pl;
+    uint32_t x = pixel % width, y = pixel / width;           // main.cpp:274-275
+    PathRng r;
+    rng_seed(r, sample_seed(prm.base_seed, pixel, samp));
+    float jy = rng_float11(r);                               // y takes the first draw
+    float jx = rng_float11(r);
+    f3 org, dir;
+    camera_ray(cam, (float)x + jx * jitter_scale, (float)y + jy * jitter_scale, org, dir);
+    q.o[s] = mk4(org, 0.0f);
+    q.d[s] = mk4u(dir, s);
+    P.rng_seed[s] = r.seed;
+    rng_store(P, s, r);
+    P.acc[s] = make_float4(0, 0, 0, 0);
+    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)prm.bounce_depth));
+    P.sp[s] = 0;
+    if (s == 0) *n_rays_out = n_slots;
+}
+
+// paths started from caller-supplied rays and seeds (rt_trace_color <-> TraceRayColor)
+__global__ void k_paths_from_rays(DevParams prm, PathPool P, RayQueue q, uint32_t n, const float *rays, const uint64_t *seeds,
+                                  uint32_t *n_rays_out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const float *rp = rays + 6 * (size_t)s;
+    q.o[s] = make_float4(rp[0], rp[1], rp[2], 0.0f);
+    q.d[s] = make_float4(rp[3], rp[4], rp[5], __uint_as_float(s));
+    PathRng r;
+    rng_seed(r, seeds[s]);
+    P.rng_seed[s] = r.seed;
+    rng_store(P, s, r);
+    P.acc[s] = make_float4(0, 0, 0, 0);
+    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)prm.bounce_depth));
+    P.sp[s] = 0;
+    if (s == 0) *n_rays_out = n;
+}
+
+// ---- K5: texture.cpp:5-83 --------------------------------------------------------------------------
+RT_DEVICE float wrap_uv(float uv) { return uv >= 0.0f ? fmodf(uv, 1.0f) : 1.0f + fmodf(uv, 1.0f); }
+
+RT_DEVICE f3 get_texel(const DevScene &S, const DevTexture &t, uint32_t x, uint32_t y) {      // texture.cpp:17-51 (xyz only)
+    const uint8_t *p = S.texels + t.offset + (size_t)(y * t.size_x + x) * t.channels;
+    uint32_t r = p[0], g = 0, b = 0;
+    if (t.channels >= 2) g = p[1];
+    if (t.channels >= 3) b = p[2];
+    if (t.channels == 1) { g = r; b = r; }
+    return mk3(__ldg(S.srgb_lut + r), __ldg(S.srgb_lut + g), __ldg(S.srgb_lut + b));
+}
+RT_DEVICE f3 lerp3(f3 a, f3 b, float t) { return a + (b - a) * t; }                           // mathlib.h:10
+
+RT_DEVICE f3 tex_sample(const DevScene &S, int tex, float u, float v) {                        // texture.cpp:53-83
+    DevTexture t = S.textures[tex];
+    u = wrap_uv(u);
+    v = 1.0f - wrap_uv(v);
+    float sx = (float)(t.size_x - 2u);
+    float sy = (float)(t.size_y - 2u);
+    float tx = clampf(u * sx, 0.0f, sx);
+    float ty = clampf(v * sy, 0.0f, sy);
+    uint32_t tx0 = (uint32_t)floorf(tx), ty0 = (uint32_t)floorf(ty);
+    uint32_t tx1 = tx0 + 1u, ty1 = ty0 + 1u;
+    float fx = tx - (float)tx0;
+    float fy = ty - (float)ty0;
+    f3 s00 = get_texel(S, t, tx0, ty0);
+    f3 s01 = get_texel(S, t, tx0, ty1);
+    f3 s10 = get_texel(S, t, tx1, ty0);
+    f3 s11 = get_texel(S, t, tx1, ty1);
+    return lerp3(lerp3(s00, s01, fy), lerp3(s10, s11, fy), fx);
+}
+
+// ---- raytracer.cpp:302-371 ---------------------------------------------------------------------------
+RT_DEVICE f3 to_world(f3 normal, f3 local) {                                                   // raytracer.cpp:306-312
+    f3 up = fabsf(normal.z) < 0.9999f ? mk3(0.0f, 0.0f, 1.0f) : mk3(1.0f, 0.0f, 0.0f);
+    f3 tangent = normalize3(cross3(up, normal));
+    f3 bitangent = normalize3(cross3(normal, tangent));
+    return normalize3((tangent * local.x + bitangent * local.y) + normal * local.z);
+}
+RT_DEVICE f3 reflect3(f3 v, f3 n) { return ((n * 2.0f) * dot3(v, n)) - v; }                    // raytracer.cpp:343-346
+RT_DEVICE float fresnel_amount(float ior_exit, float ior_enter, f3 normal, f3 incident) {      // raytracer.cpp:348-371
+    float r0 = (ior_exit - ior_enter) / (ior_exit + ior_enter);
+    r0 *= r0;
+    float ct = max0(-dot3(normal, incident));
+    if (ior_exit > ior_enter) {
+        float n = ior_exit / ior_enter;
+        float st_sq = n * n * (1.0f - ct * ct);
+        if (st_sq > 1.0f) return 1.0f;
+        ct = sqrtf(1.0f - st_sq);
+    }
+    float x = 1.0f - ct;
+    float x2 = x * x;
+    float x3 = x * x2;
+    return r0 + (1.0f - r0) * x2 * x3;
+}
+// powf(Max(0, spec_cos), Ns) (raytracer.cpp:388, 403). glibc's powf is not reproducible bit-for-bit on the GPU;
+// the double-precision pow rounded to float is within 1 ulp of it and only scales a colour (never control flow).
+RT_DEVICE float phong_pow(float x, float e) { return (float)pow((double)x, (double)e); }
+
+struct ShadowQueue { RayQueue q; float4 *rad; uint32_t *count; };
+
+// ---- K4 + K6: the coroutine step --------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
+                                              uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh) {
+    uint32_t n_in = min(*n_in_ptr, n_in_max);
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < n_in;
+    const uint32_t cap = P.capacity;
+    const int bd = (int)prm.bounce_depth;
+
+    uint32_t slot = 0, sp = 0;
+    int iters = 0;
+    f3 T = mk3(0, 0, 0), acc = mk3(0, 0, 0);
+    PathRng rng; rng.cur = 0; rng.x = 0; rng.seed = 0; rng.n = 0;
+    bool emit = false;
+    f3 e_org = mk3(0, 0, 0), e_dir = mk3(0, 0, 0), e_T = mk3(0, 0, 0);
+    int e_iters = 0;
+
+    // shadow rays of this node (one per light), pushed after the divergent part
+    bool shade_hit = false;
+    f3 hit_p = mk3(0, 0, 0), N = mk3(0, 0, 0), V = mk3(0, 0, 0), Ta = mk3(0, 0, 0), kd = mk3(0, 0, 0), ks = mk3(0, 0, 0);
+    float spec_int = 0.0f, w_diffuse = 0.0f;
+
+    if (active) {
+        float4 o4 = qin.o[i], d4 = qin.d[i];
+        slot = __float_as_uint(d4.w);
+        HitRec h = hits[i];
+        float4 t4 = P.node_T[slot];
+        T = mk3(t4); iters = __float_as_int(t4.w);
+        acc = mk3(P.acc[slot]);
+        sp = P.sp[slot];
+        rng_load(P, slot, rng);
+        f3 org = mk3(o4); V = mk3(d4);
+
+        if (h.tri < 0) {
+            acc = acc + T * mk3(prm.bg[0], prm.bg[1], prm.bg[2]);          // raytracer.cpp:573-575
+        } else {
+            const float4 *tp = reinterpret_cast<const float4 *>(S.tris + h.tri);
+            float4 r0 = __ldg(tp);
+            f3 ob = org + V * prm.ray_bias;                                  // raytracer.cpp:163
+            f3 position = ob + V * h.t;                                      // raytracer.cpp:121
+            f3 gn = normalize3(mk3(r0.x, r0.y, r0.z));                        // raytracer.cpp:122
+            hit_p = position + gn * prm.ray_bias;                            // raytracer.cpp:425
+            float4 ua = __ldg(S.tri_uv + 2 * (size_t)h.tri), ub = __ldg(S.tri_uv + 2 * (size_t)h.tri + 1);
+            int mat_id = __float_as_int(ub.z);
+            DevMaterial M = S.materials[mat_id];
+            float bwy = h.v, bwz = h.w;
+            float bwx = 1.0f - bwy - bwz;                                    // raytracer.cpp:120
+            float u = 0.0f + ua.x * bwx; u = u + ua.z * bwy; u = u + ub.x * bwz;   // raytracer.cpp:439-442
+            float v = 0.0f + ua.y * bwx; v = v + ua.w * bwy; v = v + ub.y * bwz;
+            float alpha = M.alpha;
+            bool restart = false;
+            if (M.alpha <= 1.0f || M.tex_alpha >= 0) {                       // raytracer.cpp:443-453
+                if (M.tex_alpha >= 0) alpha *= tex_sample(S, M.tex_alpha, u, v).x;
+                if (alpha <= 0.05f) restart = true;
+            }
+            if (restart) {
+                // tail call TraceRayColor(ray, iters): its Russian roulette runs again unless this is the root level
+                if (!(iters != bd && rng_float01(rng) < 0.5f)) {
+                    emit = true;
+                    e_org = position + (V * prm.ray_bias) * 2.0f;            // raytracer.cpp:450
+                    e_dir = V; e_T = T; e_iters = iters;
+                }
+            } else {
+                f3 ambient = mk3(M.ambient[0], M.ambient[1], M.ambient[2]);
+                kd = mk3(M.diffuse[0], M.diffuse[1], M.diffuse[2]);
+                ks = mk3(M.specular[0], M.specular[1], M.specular[2]);
+                if (M.tex_ambient >= 0) ambient = ambient * tex_sample(S, M.tex_ambient, u, v);      // raytracer.cpp:454-462
+                if (M.tex_diffuse >= 0) kd = kd * tex_sample(S, M.tex_diffuse, u, v);
+                if (M.tex_specular >= 0) ks = tex_sample(S, M.tex_specular, u, v);
+                const float4 *np = S.tri_nrm + 3 * (size_t)h.tri;
+                f3 n = mk3(0, 0, 0);                                          // raytracer.cpp:464-467
+                n = n + mk3(__ldg(np)) * bwx; n = n + mk3(__ldg(np + 1)) * bwy; n = n + mk3(__ldg(np + 2)) * bwz;
+                N = normalize3(n);
+                if (M.tex_bump >= 0) {                                       // raytracer.cpp:468-502
+                    const float4 *gp = S.tri_tan + 3 * (size_t)h.tri;
+                    f3 tg = mk3(0, 0, 0);
+                    tg = tg + mk3(__ldg(gp)) * bwx; tg = tg + mk3(__ldg(gp + 1)) * bwy; tg = tg + mk3(__ldg(gp + 2)) * bwz;
+                    tg = normalize3(tg);
+                    f3 bt = normalize3(cross3(N, tg));
+                    f3 sn = tex_sample(S, M.tex_bump, u, v) * 2.0f - mk3(1.0f, 1.0f, 1.0f);
+                    f3 wn;
+                    wn.x = tg.x * sn.x + bt.x * sn.y + N.x * sn.z;
+                    wn.y = tg.y * sn.x + bt.y * sn.y + N.y * sn.z;
+                    wn.z = tg.z * sn.x + bt.z * sn.y + N.z * sn.z;
+                    N = wn;                                                  // not re-normalised (raytracer.cpp:494-495)
+                }
+                spec_int = M.specular_intensity;
+                float object_reflectivity = 0.04f;                           // raytracer.cpp:538-541
+                float fres = fresnel_amount(1.0f, M.index_of_refraction, N, V);
+                float w_reflect = (object_reflectivity + (1.0f - object_reflectivity) * fres);
+                w_diffuse = 1.0f - w_reflect;
+                bool translucent = alpha < 1.0f;                             // raytracer.cpp:547-552
+                Ta = translucent ? T * alpha : T;
+                acc = acc + Ta * (ambient * 0.1f);                            // raytracer.cpp:543
+                shade_hit = true;
+                if (iters > 0) {
+                    // children exist: push this node's recursion frame
+                    f3 Td = (Ta * kd) * w_diffuse;                           // raytracer.cpp:544
+                    f3 Ts = Ta * ks;                                         // raytracer.cpp:545
+                    f3 co = position + (V * prm.ray_bias) * 2.0f;            // raytracer.cpp:549
+                    f3 Tc = T * (1.0f - alpha);
+                    uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u);   // child index 0 in bits 8..30
+                    float4 *F = P.frames + (size_t)(sp * RT_FRAME_F4) * cap + slot;
+                    F[0 * (size_t)cap] = mk4u(hit_p, meta);
+                    F[1 * (size_t)cap] = mk4u(N, (uint32_t)mat_id);
+                    F[2 * (size_t)cap] = mk4(V, spec_int);
+                    F[3 * (size_t)cap] = mk4(Td, Tc.x);
+                    F[4 * (size_t)cap] = mk4(Ts, Tc.y);
+                    F[5 * (size_t)cap] = mk4(co, Tc.z);
+                    sp++;
+                }
+                // iters == 0: the translucent continuation has iters - 1 < 0 and returns black (raytracer.cpp:416)
+            }
+        }
+
+        // walk the recursion forward to the next ray that has to be traced
+        while (!emit && sp > 0) {
+            float4 *F = P.frames + (size_t)((sp - 1) * RT_FRAME_F4) * cap + slot;
+            float4 f0 = F[0];
+            uint32_t meta = __float_as_uint(f0.w);
+            uint32_t child = (meta >> 8) & 0x7FFFFFu;
+            int f_iters = (int)(meta & 0xFFu);
+            bool has_cont = (meta & 0x80000000u) != 0;
+            uint32_t rs = prm.reflection_samples, ss = prm.spec_samples;
+            if (child >= rs + ss + (has_cont ? 1u : 0u)) { sp--; continue; }
+            F[0].w = __uint_as_float((meta & 0x800000FFu) | ((child + 1u) << 8));
+            f3 fp = mk3(f0);
+            float4 f1 = F[1 * (size_t)cap];
+            f3 fn = mk3(f1);
+            f3 c_dir, c_T, c_org = fp;
+            if (child < rs) {                                                // raytracer.cpp:516-526
+                uint32_t series_i = (uint32_t)(rng_next(rng) % 1024ull);
+                c_dir = to_world(fn, mk3(__ldg(S.hamm_dir + series_i)));
+                float4 f3v = F[3 * (size_t)cap];
+                c_T = mk3(f3v) * max0(dot3(fn, c_dir));
+            } else if (child < rs + ss) {                                    // raytracer.cpp:528-535
+                uint32_t mat_id = __float_as_uint(f1.w);
+                c_dir = to_world(fn, mk3(__ldg(S.spec_dir + (size_t)mat_id * ss + (child - rs))));
+                float4 f2 = F[2 * (size_t)cap], f4 = F[4 * (size_t)cap];
+                c_T = mk3(f4) * max0(dot3(c_dir, neg3(mk3(f2))));
+            } else {                                                         // raytracer.cpp:547-551
+                float4 f2 = F[2 * (size_t)cap], f3v = F[3 * (size_t)cap], f4 = F[4 * (size_t)cap], f5 = F[5 * (size_t)cap];
+                c_dir = mk3(f2); c_org = mk3(f5); c_T = mk3(f3v.w, f4.w, f5.w);
+            }
+            // child node entry (raytracer.cpp:416-420): iters - 1 >= 0 here, and never the root level
+            if (rng_float01(rng) < 0.5f) continue;
+            emit = true; e_org = c_org; e_dir = c_dir; e_T = c_T; e_iters = f_iters - 1;
+        }
+
+        P.acc[slot] = mk4(acc, 0.0f);
+        P.sp[slot] = sp;
+        rng_store(P, slot, rng);
+        if (emit) P.node_T[slot] = mk4(e_T, __int_as_float(e_iters));
+    }
+
+    // K6: compaction -- the next wave's queue holds only rays that exist
+    uint32_t pos = warp_push(n_out, emit);
+    if (emit) { qout.o[pos] = mk4(e_org, 0.0f); qout.d[pos] = mk4u(e_dir, slot); }
+
+    // ShadeLight (raytracer.cpp:378-411): everything but the visibility test is evaluated here
+    for (uint32_t l = 0; l < S.n_lights; ++l) {
+        bool push = shade_hit;
+        f3 lv = mk3(0, 0, 0), rad = mk3(0, 0, 0);
+        float dist_sq = -1.0f;
+        if (push) {
+            DevLight L = S.lights[l];
+            f3 lc = mk3(L.color[0], L.color[1], L.color[2]);
+            if (L.type == 0) {
+                lv = mk3(L.facing[0], L.facing[1], L.facing[2]) * -1.0f;     // raytracer.cpp:240
+            } else {
+                f3 lp = mk3(L.position[0], L.position[1], L.position[2]);
+                lv = normalize3(lp - hit_p);                                 // raytracer.cpp:243
+                f3 dv = lp - hit_p;
+                dist_sq = dot3(dv, dv);
+                float fd = (sqrtf(dist_sq) / L.falloff) + 1.0f;              // raytracer.cpp:398-399
+                lc = lc * (1.0f / (fd * fd));
+            }
+            float spec_cos = dot3(V * -1.0f, reflect3(lv, N));               // raytracer.cpp:386-388
+            f3 dd = (lc * 2.0f) * max0(dot3(N, lv));
+            f3 ds = lc * phong_pow(max0(spec_cos), spec_int);
+            rad = Ta * (((dd * kd) * w_diffuse) + ds * ks);                  // raytracer.cpp:544-545
+        }
+        uint32_t spos = warp_push(sh.count, push);
+        if (push) {
+            sh.q.o[spos] = mk4u(hit_p, slot);
+            sh.q.d[spos] = mk4(lv, dist_sq);
+            sh.rad[spos] = mk4(rad, 0.0f);
+        }
+    }
+}
+
+// ---- K7: accumulate / resolve (main.cpp:242, 262-263) -----------------------------------------------
+// accum[p] continues RenderPixel's `color += scratch[samp]` in sample order across sample sub-batches.
+__global__ void k_resolve(const float4 *acc, uint32_t n_pixels, uint32_t spp, float4 *accum, uint32_t pixel_local0) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    float4 c = accum[pixel_local0 + p];
+    for (uint32_t s = 0; s < spp; ++s) {
+        float4 a = acc[(size_t)p * spp + s];
+        c.x += a.x; c.y += a.y; c.z += a.z;
+    }
+    accum[pixel_local0 + p] = c;
+}
+
+// per-sample colours of one batch, copied out for the adaptive loop's variance test
+__global__ void k_finalize(const float4 *accum, uint32_t n_pixels, uint32_t n_samples, const uint32_t *per_pixel_samples, uint32_t flags,
+                           float4 *out, const uint32_t *pixel_ids_dev, uint32_t pixel_begin) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    float4 c = accum[p];
+    uint32_t ns = per_pixel_samples ? per_pixel_samples[p] : n_samples;
+    float4 r;
+    if (flags & 1u) { r = make_float4(c.x, c.y, c.z, (float)ns); }       // RT_OUT_SUM
+    else { float fs = (float)ns; r = make_float4(c.x / fs, c.y / fs, c.z / fs, 1.0f); }   // main.cpp:262-263
+    size_t dst = (flags & 2u) ? (size_t)(pixel_ids_dev ? pixel_ids_dev[p] : pixel_begin + p) : (size_t)p;
+    out[dst] = r;
+}
+
+// RaycastHit (raytracer.cpp:20-30) for the API: position / normal / bw / vertex0 / object from a HitRec
+struct ApiHit { float t; float bw[3]; uint32_t vertex0; float position[3]; float normal[3]; int32_t object; uint32_t hit; };
+static_assert(sizeof(ApiHit) == 52, "rt_hit layout");
+
+__global__ void k_hits_to_api(DevScene S, float bias, RayQueue q, const HitRec *hits, uint32_t n, ApiHit *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    HitRec h = hits[i];
+    ApiHit a;
+    a.t = h.t; a.hit = h.tri >= 0 ? 1u : 0u; a.object = -1; a.vertex0 = 0;
+    a.bw[0] = a.bw[1] = a.bw[2] = 0.0f;
+    a.position[0] = a.position[1] = a.position[2] = 0.0f;
+    a.normal[0] = a.normal[1] = a.normal[2] = 0.0f;
+    if (h.tri >= 0) {
+        f3 org = mk3(q.o[i]), dir = mk3(q.d[i]);
+        f3 ob = org + dir * bias;
+        f3 pos = ob + dir * h.t;
+        float4 r0 = S.tris[h.tri].r0;
+        f3 gn = normalize3(mk3(r0.x, r0.y, r0.z));
+        a.bw[1] = h.v; a.bw[2] = h.w; a.bw[0] = 1.0f - h.v - h.w;
+        a.position[0] = pos.x; a.position[1] = pos.y; a.position[2] = pos.z;
+        a.normal[0] = gn.x; a.normal[1] = gn.y; a.normal[2] = gn.z;
+        a.vertex0 = S.tri_vertex0[h.tri];
+        a.object = S.tri_object[h.tri];
+    }
+    out[i] = a;
+}
+
+__global__ void k_upload_rays(const float *rays, uint32_t n, RayQueue q) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *rp = rays + 6 * (size_t)i;
+    q.o[i] = make_float4(rp[0], rp[1], rp[2], 0.0f);
+    q.d[i] = make_float4(rp[3], rp[4], rp[5], __uint_as_float(i));
+}
+
+__global__ void k_queue_to_rays(RayQueue q, uint32_t n, float *rays) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 o = q.o[i], d = q.d[i];
+    float *rp = rays + 6 * (size_t)i;
+    rp[0] = o.x; rp[1] = o.y; rp[2] = o.z; rp[3] = d.x; rp[4] = d.y; rp[5] = d.z;
+}
+
+__global__ void k_rng_kat(uint64_t seed, uint32_t n, uint64_t *out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    PathRng r;
+    rng_seed(r, seed);
+    for (uint32_t i = 0; i < n; ++i) out[i] = rng_next(r);
+}

@@ -1,0 +1,235 @@
+// rt_trace.cuh -- kernel group K3 / K3s: hierarchy traversal + ray/sphere + ray/triangle.
+//
+// Replaces TraceRay (raytracer.cpp:159-232) with its callees IntersectRaySphere (32-60),
+// IntersectRayMesh (127-157) and IntersectRayTriangle (82-125).
+//
+// What must be bit-exact and what need not be:
+//  * The TRIANGLE test decides t, the barycentrics and hit/miss; it repeats the reference's float
+//    operations in the reference's order (unfused; this TU is built with -fmad=false).
+//  * The closest hit is the lexicographic minimum of (t, rank): rank = position of the triangle in the
+//    reference's own encounter order (c1-subtree-first DFS over its hierarchy, then index order inside a
+//    group; raytracer.cpp:136, 149, 208-209, 220), so equal-t ties resolve as in the reference although
+//    our traversal order is different.
+//  * The SPHERE test only prunes. It is our own robust formulation (distance from the centre to the ray
+//    line through the perpendicular foot, FMA allowed) with a slack proportional to the distance from
+//    the ray origin, so float rounding can never prune a triangle the exact test would accept.
+#pragma once
+#include "rt_common.cuh"
+
+#define RT_STACK_MAX 64
+#define RT_CULL_SLACK 4e-6f
+
+struct RayQueue {              // SoA ray stream: 32 B per ray
+    float4 *o;                 // origin.xyz (unbiased, as handed to TraceRay), w: kernel specific
+    float4 *d;                 // direction.xyz, w: slot / flags bits
+};
+
+struct HitRec {                // 16 B per ray
+    float t;
+    float v, w;                // bw.y, bw.z numerators already divided (raytracer.cpp:118-119)
+    int32_t tri;               // cluster-order triangle index, -1 = miss
+};
+
+struct TraceCounters { unsigned long long sphere_checks, cluster_checks; };
+
+RT_DEVICE float approx_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Conservative ray / bounding-sphere test. Returns true and the (clamped) entry distance in ray
+// parameter units when the sphere, fattened by RT_CULL_SLACK * (|m|_1 + r), can contain a hit with
+// parameter in [0, tmax].
+RT_DEVICE bool cull_sphere(float4 s, f3 o, f3 d, float inv_dd, float tmax, float &t_entry) {
+    float mx = s.x - o.x, my = s.y - o.y, mz = s.z - o.z;
+    float b = __fmaf_rn(mz, d.z, __fmaf_rn(my, d.y, mx * d.x));
+    float tca = b * inv_dd;
+    float px = __fmaf_rn(-tca, d.x, mx), py = __fmaf_rn(-tca, d.y, my), pz = __fmaf_rn(-tca, d.z, mz);
+    float dist2 = __fmaf_rn(pz, pz, __fmaf_rn(py, py, px * px));
+    float r = __fmaf_rn(RT_CULL_SLACK, fabsf(mx) + fabsf(my) + fabsf(mz) + s.w, s.w);
+    float h2 = __fmaf_rn(r, r, -dist2);
+    if (!(h2 >= 0.0f)) return false;                    // also rejects NaN radii (empty child)
+    float half = approx_sqrt(h2 * inv_dd);
+    float t0 = tca - half;
+    if (tca + half < 0.0f) return false;                // sphere entirely behind the origin
+    if (t0 > tmax) return false;                        // raytracer.cpp:177 (strict >)
+    t_entry = t0;
+    return true;
+}
+
+struct RayCtx {
+    f3 o;      // biased origin (raytracer.cpp:163)
+    f3 d;
+    f3 qp;     // o - (o + d)   (raytracer.cpp:88-89: NOT -d in floats)
+};
+
+// IntersectRayTriangle (raytracer.cpp:82-125) on a precomputed record. Returns true when the triangle is
+// hit at all; t/v/w are the reference's out_hit->t, bw.y, bw.z.
+RT_DEVICE bool tri_test(const TriRec &r, const RayCtx &c, float &t_out, float &v_out, float &w_out) {
+    f3 n = mk3(r.r0.x, r.r0.y, r.r0.z);
+    float dd = dot3(c.qp, n);
+    if (dd <= 0.0f) return false;
+    f3 a = mk3(r.r0.w, r.r1.x, r.r1.y);
+    f3 ap = c.o - a;
+    float t = dot3(ap, n);
+    if (t < 0.0f) return false;
+    f3 e = cross3(c.qp, ap);
+    f3 ac = mk3(r.r2.y, r.r2.z, r.r2.w);
+    float v = dot3(ac, e);
+    if (v < 0.0f || v > dd) return false;
+    f3 ab = mk3(r.r1.z, r.r1.w, r.r2.x);
+    float w = -dot3(ab, e);
+    if (w < 0.0f || (v + w) > dd) return false;
+    float ood = 1.0f / dd;
+    t_out = t * ood;
+    v_out = v * ood;
+    w_out = w * ood;
+    return true;
+}
+
+template <bool ANY_HIT, bool COUNT>
+RT_DEVICE void trace_one(const DevScene &S, float bias, f3 org, f3 dir, HitRec &best, uint32_t &best_rank,
+                         unsigned long long &n_sph, unsigned long long &n_clu) {
+    RayCtx c;
+    c.d = dir;
+    c.o = org + dir * bias;                              // raytracer.cpp:163
+    f3 q = c.o + dir;
+    c.qp = c.o - q;
+    float dd = __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x));
+    float inv_dd = 1.0f / dd;
+    best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1;   // raytracer.cpp:166
+    best_rank = 0xFFFFFFFFu;
+    if (S.n_tris == 0) return;
+    int stack[RT_STACK_MAX];
+    int sp = 0;
+    int cur = S.root;
+    while (true) {
+        while (cur >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
+            float4 s0 = __ldg(np), s1 = __ldg(np + 1);
+            int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 2));
+            float t0, t1;
+            // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
+            bool h0 = cull_sphere(s0, c.o, c.d, inv_dd, best.t, t0);
+            bool h1 = cull_sphere(s1, c.o, c.d, inv_dd, best.t, t1);
+            if (COUNT) n_sph += 2;
+            if (h0 && h1) {
+                int near = ch.x, far = ch.y;
+                if (t1 < t0) { near = ch.y; far = ch.x; }
+                if (sp < RT_STACK_MAX) stack[sp++] = far;
+                cur = near;
+            } else if (h0) cur = ch.x;
+            else if (h1) cur = ch.y;
+            else {
+                if (sp == 0) return;
+                cur = stack[--sp];
+            }
+        }
+        // cluster (leaf): linear scan like IntersectRayMesh (raytracer.cpp:136-154), <= RT_LEAF_MAX triangles
+        {
+            uint32_t first = leaf_first(cur), cnt = leaf_count(cur);
+            if (COUNT) n_clu += 1;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                uint32_t ti = first + k;
+                const float4 *tp = reinterpret_cast<const float4 *>(S.tris + ti);
+                TriRec r; r.r0 = __ldg(tp); r.r1 = __ldg(tp + 1); r.r2 = __ldg(tp + 2);
+                float t, v, w;
+                if (tri_test(r, c, t, v, w)) {
+                    if (t <= best.t && t < FLT_MAX) {           // t < FLT_MAX: raytracer.cpp:149/220 against { FLT_MAX }
+                        uint32_t rk = __ldg(S.tri_rank + ti);
+                        if (t < best.t || rk < best_rank) { best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk; }
+                        if (ANY_HIT) return;
+                    }
+                }
+            }
+        }
+        if (sp == 0) return;
+        cur = stack[--sp];
+    }
+}
+
+// ---- closest hit over a ray queue ----------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_closest(DevScene S, float bias, RayQueue q, const uint32_t *n_rays_ptr, uint32_t n_rays_max,
+                                                      HitRec *hits, TraceCounters *counters) {
+    uint32_t n = n_rays_ptr ? min(*n_rays_ptr, n_rays_max) : n_rays_max;
+    unsigned long long n_sph = 0, n_clu = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 o = q.o[i], d = q.d[i];
+        HitRec h; uint32_t rk;
+        trace_one<false, COUNT>(S, bias, mk3(o), mk3(d), h, rk, n_sph, n_clu);
+        hits[i] = h;
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) { n_sph += __shfl_down_sync(0xffffffffu, n_sph, o); n_clu += __shfl_down_sync(0xffffffffu, n_clu, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&counters->sphere_checks, n_sph); atomicAdd(&counters->cluster_checks, n_clu); }
+    }
+}
+
+// ---- shadow rays (ShadeLight, raytracer.cpp:378-411) ---------------------------------------------------
+// o.w = slot bits, d.w = light_dist_sq for point lights (closest hit needed, raytracer.cpp:395-396) or < 0
+// for directional lights (boolean occlusion: TraceRay's return value, raytracer.cpp:385).
+// rad = radiance to add to the path's accumulator when the light is visible.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_shadow(DevScene S, float bias, RayQueue q, const float4 *rad, const uint32_t *n_rays_ptr,
+                                                     uint32_t n_rays_max, float4 *acc, int use_atomics, TraceCounters *counters) {
+    uint32_t n = n_rays_ptr ? min(*n_rays_ptr, n_rays_max) : n_rays_max;
+    unsigned long long n_sph = 0, n_clu = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 o = q.o[i], d = q.d[i];
+        HitRec h; uint32_t rk;
+        bool lit;
+        if (d.w < 0.0f) {
+            trace_one<true, COUNT>(S, bias, mk3(o), mk3(d), h, rk, n_sph, n_clu);
+            lit = h.tri < 0;
+        } else {
+            trace_one<false, COUNT>(S, bias, mk3(o), mk3(d), h, rk, n_sph, n_clu);
+            lit = h.tri < 0 || h.t * h.t <= d.w;
+        }
+        if (lit) {
+            uint32_t slot = __float_as_uint(o.w);
+            float4 r = rad[i];
+            if (use_atomics) {
+                atomicAdd(&acc[slot].x, r.x); atomicAdd(&acc[slot].y, r.y); atomicAdd(&acc[slot].z, r.z);
+            } else {
+                float4 a = acc[slot];
+                a.x += r.x; a.y += r.y; a.z += r.z;
+                acc[slot] = a;
+            }
+        }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) { n_sph += __shfl_down_sync(0xffffffffu, n_sph, o); n_clu += __shfl_down_sync(0xffffffffu, n_clu, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&counters->sphere_checks, n_sph); atomicAdd(&counters->cluster_checks, n_clu); }
+    }
+}
+
+// boolean occlusion for the API (rt_trace_rays, RT_TRACE_ANY): tri >= 0 <=> TraceRay would return true
+__global__ void __launch_bounds__(128) k_trace_any(DevScene S, float bias, RayQueue q, uint32_t n, HitRec *hits) {
+    unsigned long long a = 0, b = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        HitRec h; uint32_t rk;
+        trace_one<true, false>(S, bias, mk3(q.o[i]), mk3(q.d[i]), h, rk, a, b);
+        hits[i] = h;
+    }
+}
+
+// brute force over every triangle: test-only cross-check of the hierarchy's conservativeness
+__global__ void k_trace_brute(DevScene S, float bias, RayQueue q, uint32_t n, HitRec *hits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 o4 = q.o[i], d4 = q.d[i];
+    RayCtx c;
+    c.d = mk3(d4);
+    c.o = mk3(o4) + c.d * bias;
+    f3 qq = c.o + c.d;
+    c.qp = c.o - qq;
+    HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
+    uint32_t best_rank = 0xFFFFFFFFu;
+    for (uint32_t ti = 0; ti < S.n_tris; ++ti) {
+        TriRec r = S.tris[ti];
+        float t, v, w;
+        if (tri_test(r, c, t, v, w) && t <= best.t && t < FLT_MAX) {
+            uint32_t rk = S.tri_rank[ti];
+            if (t < best.t || rk < best_rank) { best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk; }
+        }
+    }
+    hits[i] = best;
+}
