@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric (Mrays/s, primary + secondary; ms/frame) on BASELINE config 2:
+tessellated spheres + plane (63,490 triangles, 17 mesh groups), 1920x1080, 64 spp fixed, reference defaults
+(bounce_depth 2, 1 diffuse + 1 specular sample, 1 directional light).
+
+A "step" is one Render() of that frame. A "ray" is one TraceRay call (raytracer.cpp:161): primary, shadow,
+diffuse / specular bounce and alpha continuation rays.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--partition samples|tiles]
+
+N > 1 (torchrun, one rank per GPU): weak scaling by sample-index ranges -- rank r renders samples
+[64 r, 64 (r+1)) of every pixel as raw sums, then ONE NCCL reduce(SUM) of the 33 MB accumulation frames
+replaces the reference's MPI_Gather (main.cpp:345-347); `--partition tiles` splits the 64-spp frame into
+interleaved tiles instead (strong scaling). The reduce is inside the timed region.
+
+--impl reference: times the reference's own CPU implementation (oracle/_ref = unmodified reference compiled
+in the authoring container; else the C oracle port) on all host cores, on a bounded pixel subset.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, SPP = 1920, 1080, 64
+WORKLOAD = "config2: 16 tessellated spheres + plane, 63490 triangles / 17 groups, 1920x1080, 64 spp, bounce_depth 2"
+
+
+def b_ray(n_tris: int) -> int:
+    """algorithmic bytes per ray = 64 (ray w+r) + 32 (hit w+r) + 32 * ceil(log2(N/4)) (nodes)
+    + 4 * 36 (leaf triangles) + 88 (amortised shading traffic)."""
+    return 64 + 32 + 32 * math.ceil(math.log2(max(2.0, n_tris / 4.0))) + 144 + 88
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (or the oracle port) on the host cores
+# -------------------------------------------------------------------------------------------------
+def cpu_arm(scene_data, cam, params, budget_s: float, steps: int = 1, warmup: int = 0):
+    """Times the seeded CPU render on a pixel subset (every 24th pixel in x and y of the 1080p frame), spp
+    chosen by a 1-spp pilot so that one step is about `budget_s` seconds. Returns a dict."""
+    from oracle import oracle, ref_harness
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    xs = np.arange(12, WIDTH, 24, dtype=np.uint32)
+    ys = np.arange(12, HEIGHT, 24, dtype=np.uint32)
+    ids = (ys[:, None] * np.uint32(WIDTH) + xs[None, :]).reshape(-1).astype(np.uint32)
+    seed = int(params["base_seed"])
+    if ref_harness.available():
+        kind = "reference"
+        from par_raytracer_b200 import scenes
+        d = tempfile.mkdtemp(prefix="bench_ref_scene_")
+        scenes.write_obj(scene_data, d)
+        R = ref_harness.get()
+        R.load_scene(d)
+        R.set_params(params)
+        R.set_lights(scene_data.lights)
+
+        def run(spp):
+            _, _, cnt, sec = R.render_seeded(cam, WIDTH, HEIGHT, ids, 0, len(ids), 0, spp, spp, seed, threads=cores)
+            return int(cnt["ray_count"]), sec
+    else:
+        kind = "port"
+        O = oracle.OracleScene(scene_data)
+
+        def run(spp):
+            p = params.copy(); p["min_samples"] = p["max_samples"] = spp
+            _, _, cnt, sec = O.render(cam, p, WIDTH, HEIGHT, pixel_ids=ids, threads=cores)
+            return int(cnt["ray_count"]), sec
+    rays1, sec1 = run(1)
+    spp = int(max(1, min(SPP, round(budget_s / max(sec1, 1e-6)))))
+    for _ in range(warmup):
+        run(spp)
+    tot_r, tot_s = 0, 0.0
+    for _ in range(max(1, steps)):
+        r, s = run(spp)
+        tot_r += r; tot_s += s
+    return {"value": tot_r / tot_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "sample": f"{len(ids)} pixels (every 24th in x and y of 1920x1080) x {spp} spp, {tot_r // max(1, steps)} rays/step, "
+                      f"per-(pixel,sample) seeding, {cores} threads over contiguous pixel chunks",
+            "seconds_per_step": tot_s / max(1, steps), "rays": tot_r}
+
+
+def make_inputs():
+    from par_raytracer_b200 import scenes, types
+    sd = scenes.spheres_plane_scene()
+    h = sd.camera_hint
+    cam = types.make_camera(h["fov"], WIDTH, HEIGHT, h["position"], h["facing"])
+    params = types.default_params(spp=SPP)
+    return sd, cam, params
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    sd, cam, params = make_inputs()
+    r = cpu_arm(sd, cam, params, budget_s=20.0, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "Mrays/s (primary+secondary), CPU reference path", "value": r["value"], "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * r["seconds_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm renders a bounded pixel subset of the same frame; the metric is a rate"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist_t
+    from par_raytracer_b200 import api, dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist_t.init_process_group("nccl", device_id=dev)
+    sd, cam, params = make_inputs()
+    t0 = time.time()
+    S = api.Scene(sd, device=local_rank)
+    scene_create_s = time.time() - t0
+    info = S.hierarchy_info()
+    n_tris = info["triangles"]
+    frame = torch.zeros((WIDTH * HEIGHT, 4), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    mode = args.partition if world > 1 else "samples"
+    total_spp = SPP * world if mode == "samples" else SPP
+    p_job = params.copy(); p_job["min_samples"] = p_job["max_samples"] = total_spp
+    TIMED = api.RT_FLAG_TIME_KERNELS
+
+    def step(flags_extra=0):
+        """One Render() of the frame; device-resident output (+ the NCCL combine for N > 1)."""
+        flush.zero_()
+        frame.zero_()
+        if mode == "samples":
+            s0, ns = dist.sample_partition(total_spp, rank, world)
+            out_flags = (api.RT_OUT_SUM if world > 1 else api.RT_OUT_MEAN) | api.RT_OUT_FULLFRAME
+            cnt = S.render_device(cam, p_job, WIDTH, HEIGHT, frame.data_ptr(), sample_begin=s0, sample_count=ns,
+                                  flags=out_flags | flags_extra, stream=stream)
+        else:
+            ids = dist.tile_partition(WIDTH, HEIGHT, rank, world, 32)
+            cnt = S.render_device(cam, p_job, WIDTH, HEIGHT, frame.data_ptr(), pixel_ids=ids, sample_count=total_spp,
+                                  flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME | flags_extra, stream=stream)
+        st = S.stats()
+        if world > 1:
+            dist.combine_frame(frame, mode, total_spp, dst=0)
+        return int(cnt["ray_count"]), st
+
+    def sync_all():
+        if world > 1:
+            dist_t.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rays = 0; launches = 0; trace_ms = 0.0; closest_rays = 0; shadow_ms = 0.0; logic_ms = 0.0; waves = 0; shadow_rays = 0
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        r, st = step(TIMED)
+        rays += r; launches += int(st["kernel_launches"]); trace_ms += float(st["trace_ms"]); closest_rays += int(st["closest_rays"])
+        shadow_ms += float(st["shadow_ms"]); logic_ms += float(st["logic_ms"]); waves += int(st["waves"]); shadow_rays += int(st["shadow_rays"])
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+
+    # ---- end to end through the public API: host camera/params in, host framebuffer out, every step ----
+    host_frame = torch.empty((WIDTH * HEIGHT, 4), dtype=torch.float32).pin_memory()
+    cam_h = np.asarray(cam).copy(); par_h = np.asarray(p_job).copy()
+
+    def e2e_step():
+        r, _ = step()
+        if rank == 0:
+            host_frame.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            float(host_frame[0, 0])               # the caller reads the result
+        return r
+    e2e_step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_rays = 0
+    e0.record()
+    for _ in range(args.steps):
+        e_rays += e2e_step()
+    e1.record()
+    sync_all()
+    e_ms = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, e_ms], dtype=torch.float64, device=dev)
+        dist_t.all_reduce(t, op=dist_t.ReduceOp.MAX)
+        ms, e_ms = float(t[0]), float(t[1])
+        c = torch.tensor([rays, e_rays, launches], dtype=torch.float64, device=dev)
+        dist_t.all_reduce(c, op=dist_t.ReduceOp.SUM)
+        rays, e_rays, launches = int(c[0]), int(c[1]), int(c[2])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        bytes_per_ray = b_ray(n_tris)
+        achieved = closest_rays * bytes_per_ray / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+        value = rays / (ms * 1e-3) / 1e6
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_arm(sd, cam, params, budget_s=15.0)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": "Mrays/s (primary+secondary)", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if mode == "samples" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP if mode == "samples" else SPP / world,
+                       "spp_total": total_spp, "partition": mode if world > 1 else "none",
+                       "combine": "NCCL reduce(SUM) of 33 MB float4 frames inside the timed region" if world > 1 else "none",
+                       "l2": "256 MB memset flushes L2 before every step; per-step path-state streams (~1.3 GB) exceed the 126 MB L2; the 3.9 MB scene is L2-resident by design",
+                       "triangles": n_tris, "hierarchy_nodes": info["nodes"], "scene_create_s": scene_create_s,
+                       "rays_per_step": rays // args.steps // 1, "waves_per_step": waves // args.steps,
+                       "kernel_ms_per_step": {"trace_closest": trace_ms / args.steps, "trace_shadow": shadow_ms / args.steps, "shade_logic": logic_ms / args.steps}},
+            "clocks": clocks,
+            "e2e": {"value": e_rays / (e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e_ms / args.steps,
+                    "h2d_bytes_per_step": int(cam_h.nbytes + par_h.nbytes), "d2h_bytes_per_step": int(WIDTH * HEIGHT * 16),
+                    "note": "rt_render_device + pinned-host download of the finished frame each step; the scene stays resident like the reference's loaded Scene"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_trace_closest", "bytes_per_ray": bytes_per_ray, "rays_timed": closest_rays, "kernel_ms": trace_ms,
+                         "peak_source": peak_src,
+                         "whole_step_frac": value * 1e6 / world * bytes_per_ray / (peak * 1e9)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist_t.barrier()
+        dist_t.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

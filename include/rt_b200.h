@@ -106,7 +106,9 @@ typedef struct rt_counters {
 /* device-side measurements of the last call on a scene */
 typedef struct rt_stats {
     double   gpu_ms;                        /* CUDA-event time of the render region on the scene's stream */
-    double   trace_ms;                      /* CUDA-event time summed over the trace kernels only (0 unless RT_FLAG_TIME_KERNELS) */
+    double   trace_ms;                      /* CUDA-event time summed over the closest-hit kernel launches (0 unless RT_FLAG_TIME_KERNELS) */
+    double   shadow_ms;                     /* same for the occlusion kernel launches */
+    double   logic_ms;                      /* same for the shade / bounce-generation kernel launches */
     uint64_t kernel_launches;               /* kernels launched by the call */
     uint64_t waves;                         /* wavefront iterations */
     uint64_t closest_rays;                  /* rays through the closest-hit kernel */

@@ -78,7 +78,7 @@ struct Pool {                 // per-render working set, kept between calls and 
     RayQueue q[2]{};
     HitRec *hits = nullptr;
     ShadowQueue shadow{};
-    uint32_t *counts = nullptr;        // [0],[1]: ray queue sizes (ping-pong), [2]: shadow queue size
+    uint32_t *counts = nullptr;        // [0],[1]: ray queue sizes (ping-pong), [2 + l]: shadow queue size of light l
     WaveTotals *totals = nullptr;
     TraceCounters *tcount = nullptr;
     uint32_t *h_counts = nullptr;      // pinned mirror of counts
@@ -97,6 +97,8 @@ struct rt_scene {
     rt_stats stats{};
     Pool pool;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
+    size_t tev_used = 0;
     int sm_count = 148;
 };
 
@@ -287,6 +289,7 @@ extern "C" void rt_scene_destroy(rt_scene *sc) {
     sc->mem.release();
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
+    for (cudaEvent_t e : sc->tev) cudaEventDestroy(e);
     if (sc->stream) cudaStreamDestroy(sc->stream);
     delete sc;
 }
@@ -471,9 +474,11 @@ static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
     for (int k = 0; k < 2; ++k) { CK(p.mem.alloc(&p.q[k].o, c)); CK(p.mem.alloc(&p.q[k].d, c)); }
     CK(p.mem.alloc(&p.hits, c));
     CK(p.mem.alloc(&p.shadow.q.o, c * lights)); CK(p.mem.alloc(&p.shadow.q.d, c * lights)); CK(p.mem.alloc(&p.shadow.rad, c * lights));
-    CK(p.mem.alloc(&p.counts, 4)); CK(p.mem.alloc(&p.totals, 1)); CK(p.mem.alloc(&p.tcount, 1));
+    CK(p.mem.alloc(&p.counts, 2 + lights)); CK(p.mem.alloc(&p.totals, 1)); CK(p.mem.alloc(&p.tcount, 1));
     p.shadow.count = p.counts + 2;
-    if (!p.h_counts) CK(cudaMallocHost((void **)&p.h_counts, 64));
+    p.shadow.capacity = capacity;
+    if (p.h_counts) { cudaFreeHost(p.h_counts); p.h_counts = nullptr; }
+    CK(cudaMallocHost((void **)&p.h_counts, (2 + lights) * sizeof(uint32_t)));
     p.capacity = capacity; p.depth = depth; p.lights = lights;
     return RT_OK;
 }
@@ -511,36 +516,65 @@ static int check_params(const rt_params *p) {
 // ---------------------------------------------------------------------------------------------
 struct WaveCfg { bool count; };
 
+static int wave_event(rt_scene *sc, bool on) {
+    if (!on) return RT_OK;
+    if (sc->tev_used == sc->tev.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        sc->tev.push_back(e);
+    }
+    CK(cudaEventRecord(sc->tev[sc->tev_used++], sc->stream));
+    return RT_OK;
+}
+
+// sums the per-wave event intervals recorded since tev_used was reset (stream must be idle)
+static int collect_wave_times(rt_scene *sc) {
+    for (size_t i = 0; i + 3 < sc->tev_used; i += 4) {
+        float a = 0, b = 0, c = 0;
+        CK(cudaEventElapsedTime(&a, sc->tev[i], sc->tev[i + 1]));
+        CK(cudaEventElapsedTime(&b, sc->tev[i + 1], sc->tev[i + 2]));
+        CK(cudaEventElapsedTime(&c, sc->tev[i + 2], sc->tev[i + 3]));
+        sc->stats.trace_ms += a; sc->stats.logic_ms += b; sc->stats.shadow_ms += c;
+    }
+    sc->tev_used = 0;
+    return RT_OK;
+}
+
 static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint32_t flags, uint64_t *launches) {
+    const bool timed = (flags & RT_FLAG_TIME_KERNELS) != 0;
     Pool &p = sc->pool;
     cudaStream_t st = sc->stream;
     const bool count = (flags & RT_FLAG_COUNTERS) != 0;
-    const int use_atomics = sc->n_lights > 1 ? 1 : 0;
+    const uint32_t L = sc->n_lights;
     const uint32_t max_grid = (uint32_t)sc->sm_count * 16u;
     uint32_t n = n_first;
     int cur = 0;
     while (n > 0) {
         CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
-        CK(cudaMemsetAsync(p.counts + 2, 0, 4, st));
+        if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
         uint32_t grid = std::min(cdiv(n, 128), max_grid);
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         if (count) k_trace_closest<true><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[cur], p.counts + cur, n, p.hits, p.tcount);
         else k_trace_closest<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[cur], p.counts + cur, n, p.hits, p.tcount);
         CKL("k_trace_closest");
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         k_logic<<<cdiv(n, 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, n, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
         CKL("k_logic");
-        CK(cudaMemcpyAsync(p.h_counts, p.counts, 16, cudaMemcpyDeviceToHost, st));
-        uint32_t n_sh_max = n * std::max(1u, sc->n_lights);
-        uint32_t sgrid = std::min(cdiv(n_sh_max, 128), max_grid);
-        if (sc->n_lights) {
-            if (count) k_trace_shadow<true><<<sgrid, 128, 0, st>>>(sc->d, prm.ray_bias, p.shadow.q, p.shadow.rad, p.shadow.count, n_sh_max, p.paths.acc, use_atomics, p.tcount);
-            else k_trace_shadow<false><<<sgrid, 128, 0, st>>>(sc->d, prm.ray_bias, p.shadow.q, p.shadow.rad, p.shadow.count, n_sh_max, p.paths.acc, use_atomics, p.tcount);
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
+        CK(cudaMemcpyAsync(p.h_counts, p.counts, 4 * (2 + L), cudaMemcpyDeviceToHost, st));
+        for (uint32_t l = 0; l < L; ++l) {        // at most n shadow rays per light; the kernel reads the real count on the device
+            RayQueue sq; sq.o = p.shadow.q.o + (size_t)l * p.shadow.capacity; sq.d = p.shadow.q.d + (size_t)l * p.shadow.capacity;
+            const float4 *rad = p.shadow.rad + (size_t)l * p.shadow.capacity;
+            if (count) k_trace_shadow<true><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, sq, rad, p.shadow.count + l, n, p.paths.acc, p.tcount);
+            else k_trace_shadow<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, sq, rad, p.shadow.count + l, n, p.paths.acc, p.tcount);
             CKL("k_trace_shadow");
             *launches += 1;
         }
         *launches += 2;
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         CK(cudaStreamSynchronize(st));
         sc->stats.closest_rays += n;
-        sc->stats.shadow_rays += p.h_counts[2];
+        for (uint32_t l = 0; l < L; ++l) sc->stats.shadow_rays += p.h_counts[2 + l];
         sc->stats.waves += 1;
         n = p.h_counts[cur ^ 1];
         cur ^= 1;
@@ -575,6 +609,7 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
         CK(cudaStreamWaitEvent(st, sc->ev1, 0));
     }
     memset(&sc->stats, 0, sizeof(sc->stats));
+    sc->tev_used = 0;
     uint64_t launches = 0;
     if (pixel_count == 0 || sample_count == 0) { if (out_counters) memset(out_counters, 0, sizeof(*out_counters)); return RT_OK; }
 
@@ -631,6 +666,7 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
     CKR(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
     sc->stats.gpu_ms = ms;
     sc->stats.kernel_launches = launches;
+    { int rc_ = collect_wave_times(sc); if (rc_) return done(rc_); }
     if (out_counters) {
         out_counters->ray_count = sc->stats.closest_rays + sc->stats.shadow_rays;
         out_counters->sphere_check_count = tc.sphere_checks;

@@ -166,7 +166,9 @@ RT_DEVICE float fresnel_amount(float ior_exit, float ior_enter, f3 normal, f3 in
 // the double-precision pow rounded to float is within 1 ulp of it and only scales a colour (never control flow).
 RT_DEVICE float phong_pow(float x, float e) { return (float)pow((double)x, (double)e); }
 
-struct ShadowQueue { RayQueue q; float4 *rad; uint32_t *count; };
+// One sub-queue per light (light l owns entries [l * capacity, (l + 1) * capacity) and count[l]): a path has at most one
+// ray in each, so the occlusion kernel adds to the path's accumulator without atomics and in light order.
+struct ShadowQueue { RayQueue q; float4 *rad; uint32_t *count; uint32_t capacity; };
 
 // ---- K4 + K6: the coroutine step --------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
             f3 ds = lc * phong_pow(max0(spec_cos), spec_int);
             rad = Ta * (((dd * kd) * w_diffuse) + ds * ks);                  // raytracer.cpp:544-545
         }
-        uint32_t spos = warp_push(sh.count, push);
+        uint32_t spos = warp_push(sh.count + l, push) + l * sh.capacity;
         if (push) {
             sh.q.o[spos] = mk4u(hit_p, slot);
             sh.q.d[spos] = mk4(lv, dist_sq);

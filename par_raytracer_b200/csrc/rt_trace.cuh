@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(DevScene S, float bias, R
 // rad = radiance to add to the path's accumulator when the light is visible.
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_trace_shadow(DevScene S, float bias, RayQueue q, const float4 *rad, const uint32_t *n_rays_ptr,
-                                                     uint32_t n_rays_max, float4 *acc, int use_atomics, TraceCounters *counters) {
+                                                     uint32_t n_rays_max, float4 *acc, TraceCounters *counters) {
     uint32_t n = n_rays_ptr ? min(*n_rays_ptr, n_rays_max) : n_rays_max;
     unsigned long long n_sph = 0, n_clu = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -186,13 +186,9 @@ __global__ void __launch_bounds__(128) k_trace_shadow(DevScene S, float bias, Ra
         if (lit) {
             uint32_t slot = __float_as_uint(o.w);
             float4 r = rad[i];
-            if (use_atomics) {
-                atomicAdd(&acc[slot].x, r.x); atomicAdd(&acc[slot].y, r.y); atomicAdd(&acc[slot].z, r.z);
-            } else {
-                float4 a = acc[slot];
-                a.x += r.x; a.y += r.y; a.z += r.z;
-                acc[slot] = a;
-            }
+            float4 a = acc[slot];                       // one ray per path per launch: plain read-modify-write
+            a.x += r.x; a.y += r.y; a.z += r.z;
+            acc[slot] = a;
         }
     }
     if (COUNT) {

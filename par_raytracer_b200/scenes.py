@@ -51,6 +51,9 @@ def build_group_hierarchy(positions: np.ndarray, group_first: np.ndarray, idx_po
     radii = np.zeros(G, dtype=np.float64)
     for g in range(G):
         idx = idx_positions[group_first[g]:group_first[g + 1]]
+        if idx.size == 0:                       # an empty group still owns a leaf (main.cpp:587 allows it)
+            radii[g] = 1e-3
+            continue
         p = positions[idx].astype(np.float64)
         lo, hi = p.min(axis=0), p.max(axis=0)
         c = 0.5 * (lo + hi)

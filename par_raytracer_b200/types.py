@@ -28,7 +28,7 @@ PARAMS = np.dtype([("ray_bias", "<f4"), ("reflection_samples", "<u4"), ("spec_sa
                    ("max_samples", "<u4"), ("base_seed", "<u8")])
 HIT = np.dtype([("t", "<f4"), ("bw", "<f4", 3), ("vertex0", "<u4"), ("position", "<f4", 3), ("normal", "<f4", 3),
                 ("object", "<i4"), ("hit", "<u4")])
-STATS = np.dtype([("gpu_ms", "<f8"), ("trace_ms", "<f8"), ("kernel_launches", "<u8"), ("waves", "<u8"),
+STATS = np.dtype([("gpu_ms", "<f8"), ("trace_ms", "<f8"), ("shadow_ms", "<f8"), ("logic_ms", "<f8"), ("kernel_launches", "<u8"), ("waves", "<u8"),
                   ("closest_rays", "<u8"), ("shadow_rays", "<u8"), ("h2d_bytes", "<u8"), ("d2h_bytes", "<u8")])
 
 assert RAY.itemsize == 24 and CAMERA.itemsize == 64 and BSPHERE.itemsize == 24 and LIGHT.itemsize == 48

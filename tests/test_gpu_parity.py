@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: against golden vectors produced by the
+unmodified reference, and against the C oracle on seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * integer / index / control-flow results -- hit masks, primitive ids (object, vertex0), t, barycentrics,
+    hit position and normal, generated rays, random draws, ray counts: BIT-EXACT, for primary AND secondary rays;
+  * radiance: the throughput formulation re-associates the reference's nested sums and the Phong powf is
+    CUDA's double pow rounded to float instead of glibc powf, so colours are compared with
+    rtol = 1e-5, atol = 1e-6 on linear floats (observed max relative error 3e-7) and PSNR >= 100 dB.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_hits_equal, bits
+from oracle import oracle
+from par_raytracer_b200 import api, dist, scenes, types
+from par_raytracer_b200.types import RAY
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def psnr(a, b):
+    mse = float(np.mean((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2))
+    peak = float(np.max(b[..., :3]))
+    return 10 * np.log10(peak * peak / max(mse, 1e-300))
+
+
+@pytest.fixture(scope="module")
+def gscene(golden_scene):
+    S = api.Scene(golden_scene.scene)
+    yield golden_scene, S
+    S.close()
+
+
+def test_rng_on_device(golden_functions):
+    g = golden_functions
+    for k, seed in enumerate(g["rng_seeds"]):
+        assert np.array_equal(api.rng_kat(int(seed), 48), g["rng_next"][k])        # 48 draws: crosses the 16-word ring wrap
+
+
+def test_primary_rays_and_hits_bit_exact(gscene):
+    gs, S = gscene
+    rays, hits = S.trace_primary(gs.cam, gs.params, gs.W, gs.H, sample_count=2)
+    assert rays.tobytes() == gs.primary_rays.tobytes()
+    assert_hits_equal(hits, gs.primary_hits, "primary")
+    # an explicit pixel list in arbitrary order gives the same entries
+    ids = np.random.default_rng(3).permutation(gs.W * gs.H).astype(np.uint32)[:300]
+    r2, h2 = S.trace_primary(gs.cam, gs.params, gs.W, gs.H, pixel_ids=ids, sample_count=2)
+    sel = (ids[:, None].astype(np.int64) * 2 + np.arange(2)[None, :]).reshape(-1)
+    assert r2.tobytes() == gs.primary_rays[sel].tobytes()
+    assert_hits_equal(h2, gs.primary_hits[sel], "primary/pixel list")
+
+
+def test_trace_ray_random_bit_exact(gscene):
+    gs, S = gscene
+    h, cnt = S.trace_rays(gs.params, gs.random_rays)
+    assert_hits_equal(h, gs.random_hits, "random")
+    assert cnt["ray_count"] == len(gs.random_rays)
+    hb, _ = S.trace_rays(gs.params, gs.random_rays, api.RT_TRACE_BRUTE)
+    assert_hits_equal(hb, gs.random_hits, "brute force")
+    ha, _ = S.trace_rays(gs.params, gs.random_rays, api.RT_TRACE_ANY)
+    assert np.array_equal(ha["hit"], gs.random_hits["hit"])
+
+
+def test_trace_ray_color(gscene):
+    gs, S = gscene
+    col, cnt = S.trace_color(gs.params, gs.color_rays, gs.color_seeds)
+    assert cnt["ray_count"] == gs.color_counters["ray_count"]      # every secondary ray decision identical
+    assert np.allclose(col[:, :3], gs.color_rgba[:, :3], rtol=RTOL, atol=ATOL)
+
+
+def test_render_fixed_spp(gscene):
+    gs, S = gscene
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
+    img, cnt = S.render(gs.cam, p, gs.W, gs.H)
+    want = gs.render_rgba.reshape(gs.H, gs.W, 4)
+    assert cnt["ray_count"] == gs.render_counters["ray_count"]
+    assert np.allclose(img, want, rtol=RTOL, atol=ATOL)
+    assert np.all(img[..., 3] == 1.0)
+    assert psnr(img, want) >= 100.0
+    # sample sub-range as raw sums (the sample-split mode)
+    s2, _ = S.render_task(gs.cam, p, gs.W, gs.H, sample_begin=2, sample_count=gs.render_spp, flags=api.RT_OUT_SUM)
+    assert np.allclose(s2[:, :3], gs.render_sum_from2[:, :3], rtol=RTOL, atol=ATOL)
+    assert np.all(s2[:, 3] == gs.render_spp)
+
+
+def test_render_is_deterministic_and_partition_invariant(gscene):
+    import torch
+    gs, S = gscene
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = 3
+    a, ca = S.render(gs.cam, p, gs.W, gs.H)
+    b, cb = S.render(gs.cam, p, gs.W, gs.H)
+    assert np.array_equal(bits(a), bits(b)) and ca["ray_count"] == cb["ray_count"]
+    flat = a.reshape(-1, 4)
+    # RenderTask over a sub-range == the same pixels of the full render (MPI rank semantics, main.cpp:316-317)
+    start, count = dist.range_partition(gs.W, gs.H, 1, 3)
+    part, _ = S.render_task(gs.cam, p, gs.W, gs.H, pixel_begin=start, pixel_count=count)
+    assert np.array_equal(bits(part), bits(flat[start:start + count]))
+    # tiles of 2 ranks written into zeroed full frames; their sum == the full frame bit for bit
+    frames = []
+    for r in range(2):
+        f = torch.zeros((gs.W * gs.H, 4), dtype=torch.float32, device="cuda")
+        ids = dist.tile_partition(gs.W, gs.H, r, 2, tile=8)
+        S.render_device(gs.cam, p, gs.W, gs.H, f.data_ptr(), pixel_ids=ids, sample_count=3,
+                        flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME, stream=torch.cuda.current_stream().cuda_stream)
+        frames.append(f)
+    torch.cuda.synchronize()
+    total = (frames[0] + frames[1]).cpu().numpy()
+    assert np.array_equal(bits(total), bits(flat))
+    # sample split: sums of two halves / n == full render within tolerance
+    s0, _ = S.render_task(gs.cam, p, gs.W, gs.H, sample_begin=0, sample_count=1, flags=api.RT_OUT_SUM)
+    s1, _ = S.render_task(gs.cam, p, gs.W, gs.H, sample_begin=1, sample_count=2, flags=api.RT_OUT_SUM)
+    assert np.allclose((s0 + s1)[:, :3] / 3.0, flat[:, :3], rtol=RTOL, atol=ATOL)
+
+
+def test_small_pool_batches_give_identical_results(gscene, monkeypatch):
+    """Pool smaller than the job: pixel batches and sample sub-batches must not change a single bit."""
+    gs, S = gscene
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = 5
+    a, ca = S.render(gs.cam, p, gs.W, gs.H)
+    monkeypatch.setenv("RT_B200_POOL", "777")
+    b, cb = S.render(gs.cam, p, gs.W, gs.H)
+    monkeypatch.setenv("RT_B200_POOL", "3")          # fewer slots than samples per pixel
+    c, cc = S.render_task(gs.cam, p, gs.W, gs.H, pixel_begin=100, pixel_count=40)
+    assert np.array_equal(bits(a), bits(b)) and ca["ray_count"] == cb["ray_count"]
+    assert np.array_equal(bits(c), bits(a.reshape(-1, 4)[100:140]))
+
+
+@pytest.mark.parametrize("kind", ["heightfield_tex", "spheres_tex", "spheres_plain"])
+def test_seeded_scenes_against_oracle(kind):
+    if kind == "heightfield_tex":
+        sd = scenes.heightfield_scene(64, 48, block=8, textured=True, tex_size=64)
+    elif kind == "spheres_tex":
+        sd = scenes.spheres_plane_scene(grid=3, nu=24, nv=12, textured=True)
+    else:
+        sd = scenes.spheres_plane_scene(grid=2, nu=32, nv=16)
+    S = api.Scene(sd); O = oracle.OracleScene(sd)
+    W, H = 128, 96
+    h = sd.camera_hint
+    cam = types.make_camera(h["fov"], W, H, h["position"], h["facing"])
+    p = types.default_params(spp=4, base_seed=0xA6E413E7DB131AE8)
+    rg, hg = S.trace_primary(cam, p, W, H, sample_count=3)
+    ro, ho = O.trace_primary(cam, p, W, H, None, 0, W * H, 0, 3)
+    assert rg.tobytes() == ro.tobytes()
+    assert_hits_equal(hg, ho, kind + " primary")
+    assert 0.2 < ho["hit"].mean() < 1.0
+    rng = np.random.default_rng(11)
+    n = 60000
+    rays = np.zeros(n, RAY)
+    lo, hi = sd.positions.min(0), sd.positions.max(0)
+    rays["origin"] = (lo + (hi - lo) * rng.random((n, 3)) + np.array([0, 1.5, 0])).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["direction"] = d.astype(np.float32)
+    # rays starting ON the geometry (what bounce rays look like) and grazing rays along triangle edges
+    tri = rng.integers(0, sd.n_triangles, n // 3)
+    a = sd.positions[sd.idx_positions[3 * tri]]; b = sd.positions[sd.idx_positions[3 * tri + 1]]
+    rays["origin"][: n // 3] = a
+    rays["direction"][: n // 6] = (b - a)[: n // 6] / np.maximum(1e-9, np.linalg.norm((b - a)[: n // 6], axis=1, keepdims=True))
+    hg2, _ = S.trace_rays(p, rays)
+    ho2, _ = O.trace_rays(p, rays)
+    assert_hits_equal(hg2, ho2, kind + " random")
+    img, cnt = S.render(cam, p, W, H)
+    ref, _, cnt_o, _ = O.render(cam, p, W, H, threads=8)
+    assert cnt["ray_count"] == cnt_o["ray_count"]
+    assert np.allclose(img.reshape(-1, 4), ref, rtol=RTOL, atol=ATOL)
+    S.close()
+
+
+def test_param_variants_against_oracle():
+    """bounce depth 0 / 1 / 3, several reflection and specular samples, > 15 draws per sample (ring wrap)."""
+    sd = scenes.spheres_plane_scene(grid=2, nu=16, nv=8, textured=True)
+    S = api.Scene(sd); O = oracle.OracleScene(sd)
+    W, H = 64, 48
+    h = sd.camera_hint
+    cam = types.make_camera(h["fov"], W, H, h["position"], h["facing"])
+    for bd, rs, ss in ((0, 1, 1), (1, 2, 0), (1, 0, 3), (3, 2, 2), (2, 3, 1)):
+        p = types.default_params(spp=2)
+        p["bounce_depth"] = bd; p["reflection_samples"] = rs; p["spec_samples"] = ss
+        img, cnt = S.render(cam, p, W, H)
+        ref, _, cnt_o, _ = O.render(cam, p, W, H, threads=8)
+        assert cnt["ray_count"] == cnt_o["ray_count"], (bd, rs, ss)
+        assert np.allclose(img.reshape(-1, 4), ref, rtol=RTOL, atol=ATOL), (bd, rs, ss)
+    S.close()
+
+
+def test_degenerate_scenes():
+    """Empty and tiny inputs: zero triangles, one triangle, a scene smaller than one cluster; empty jobs."""
+    cam = types.make_camera(60.0, 32, 24, (0, 0, 5), (0, 0, -1))
+    p = types.default_params(spp=2)
+    base = scenes.spheres_plane_scene(grid=1, nu=8, nv=4)
+    for ntri in (0, 1, 3):
+        mb = scenes.MeshBuilder()
+        pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0], [2, 1, -1], [3, -1, -1], [-2, 2, -2]], np.float32)
+        tris = np.array([[0, 1, 2], [1, 4, 3], [2, 3, 5]])[:ntri].reshape(-1, 3)
+        mb.add_group("g", 0, pos, pos[:, :2], np.tile(np.array([[0, 0, 1]], np.float32), (6, 1)), tris)
+        sd = mb.finish(base.materials[:1], [])
+        S = api.Scene(sd); O = oracle.OracleScene(sd)
+        rg, hg = S.trace_primary(cam, p, 32, 24, sample_count=1)
+        ro, ho = O.trace_primary(cam, p, 32, 24, None, 0, 32 * 24, 0, 1)
+        assert_hits_equal(hg, ho, f"{ntri} triangles")
+        img, cnt = S.render(cam, p, 32, 24)
+        ref, _, cnt_o, _ = O.render(cam, p, 32, 24)
+        assert cnt["ray_count"] == cnt_o["ray_count"]
+        assert np.allclose(img.reshape(-1, 4), ref, rtol=RTOL, atol=ATOL)
+        out, c0 = S.render_task(cam, p, 32, 24, pixel_begin=5, pixel_count=0)
+        assert out.shape == (0, 4) and c0["ray_count"] == 0
+        with pytest.raises(api.RtError):
+            S.render_task(cam, p, 32, 24, pixel_begin=32 * 24 - 1, pixel_count=2)      # range beyond the frame
+        S.close()
