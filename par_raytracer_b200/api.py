@@ -21,7 +21,7 @@ from .cabi import RtSceneDesc, make_scene_desc
 from .types import CAMERA, COUNTERS, HIT, PARAMS, RAY, STATS, SceneData
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 
 RT_OUT_MEAN, RT_OUT_SUM, RT_OUT_FULLFRAME, RT_FLAG_COUNTERS, RT_FLAG_TIME_KERNELS = 0, 1, 2, 4, 8
 RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2

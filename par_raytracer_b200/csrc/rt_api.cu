@@ -79,6 +79,8 @@ struct Pool {                 // per-render working set, kept between calls and 
     HitRec *hits = nullptr;
     ShadowQueue shadow{};
     uint32_t *counts = nullptr;        // [0],[1]: ray queue sizes (ping-pong), [2 + l]: shadow queue size of light l
+    float4 *acc_extra = nullptr;       // per-path accumulators of lights >= 1
+    uint32_t *next = nullptr;          // work counter of the wave trace kernel
     WaveTotals *totals = nullptr;
     TraceCounters *tcount = nullptr;
     uint32_t *h_counts = nullptr;      // pinned mirror of counts
@@ -100,6 +102,7 @@ struct rt_scene {
     std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
     size_t tev_used = 0;
     int sm_count = 148;
+    int trace_grid = 148 * 8;            // persistent grid of k_trace_wave: resident blocks of the whole chip
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -176,13 +179,13 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
 
     uint32_t n_pad = BITONIC_TILE;
     while (n_pad < n) n_pad <<= 1;
-    float4 *tri_sphere; uint32_t *bounds; uint64_t *keys; uint32_t *vals;
-    CKB(tmp.alloc(&tri_sphere, n)); CKB(tmp.alloc(&bounds, 8)); CKB(tmp.alloc(&keys, n_pad)); CKB(tmp.alloc(&vals, n_pad));
+    float4 *tri_sphere, *tri_lo, *tri_hi; uint32_t *bounds; uint64_t *keys; uint32_t *vals;
+    CKB(tmp.alloc(&tri_sphere, n)); CKB(tmp.alloc(&tri_lo, n)); CKB(tmp.alloc(&tri_hi, n)); CKB(tmp.alloc(&bounds, 8)); CKB(tmp.alloc(&keys, n_pad)); CKB(tmp.alloc(&vals, n_pad));
     {
         uint32_t hb[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
         CKB(cudaMemcpyAsync(bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
     }
-    k_tri_spheres<<<cdiv(n, 256), 256, 0, st>>>(bin, tri_sphere, bounds); CKLB("k_tri_spheres");
+    k_tri_spheres<<<cdiv(n, 256), 256, 0, st>>>(bin, tri_sphere, tri_lo, tri_hi, bounds); CKLB("k_tri_spheres");
     k_morton<<<cdiv(n_pad, 256), 256, 0, st>>>(n, n_pad, tri_sphere, bounds, keys, vals); CKLB("k_morton");
     // bitonic sort
     k_bitonic_shared<<<n_pad / BITONIC_TILE, 1024, 0, st>>>(keys, vals, 2, BITONIC_TILE, 0); CKLB("k_bitonic_shared");
@@ -198,8 +201,9 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     TempTree t;
     CKB(tmp.alloc(&t.c0, n_total)); CKB(tmp.alloc(&t.c1, n_total)); CKB(tmp.alloc(&t.parent, n_total));
     CKB(tmp.alloc(&t.size, n_total)); CKB(tmp.alloc(&t.kept, n_total)); CKB(tmp.alloc(&t.sphere, n_total));
-    float4 *cs[2]; int32_t *cn[2]; uint32_t *nn; uint64_t *flags, *scan, *bsums, *total;
-    CKB(tmp.alloc(&cs[0], n)); CKB(tmp.alloc(&cs[1], n)); CKB(tmp.alloc(&cn[0], n)); CKB(tmp.alloc(&cn[1], n));
+    CKB(tmp.alloc(&t.lo, n_total)); CKB(tmp.alloc(&t.hi, n_total));
+    int32_t *cn[2]; uint32_t *nn, *slot_tri; uint64_t *flags, *scan, *bsums, *total;
+    CKB(tmp.alloc(&cn[0], n)); CKB(tmp.alloc(&cn[1], n)); CKB(tmp.alloc(&slot_tri, n));
     CKB(tmp.alloc(&nn, n)); CKB(tmp.alloc(&flags, n)); CKB(tmp.alloc(&scan, n));
     CKB(tmp.alloc(&bsums, cdiv(n, SCAN_TILE) + 1)); CKB(tmp.alloc(&total, 1));
     uint32_t *tri_offset, *kept_index, *max_depth;
@@ -209,18 +213,18 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     int32_t root_temp = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         const int pair_mode = attempt;       // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n)
-        k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, cs[0], cn[0], t); CKLB("k_ploc_init");
+        k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, tri_lo, tri_hi, cn[0], t); CKLB("k_ploc_init");
         uint32_t m = n, created = 0;
         int cur = 0;
         iterations = 0;
         while (m > 1) {
-            k_ploc_nn<<<cdiv(m, 256), 256, 0, st>>>(m, cs[cur], nn, pair_mode); CKLB("k_ploc_nn");
+            k_ploc_nn<<<cdiv(m, 256), 256, 0, st>>>(m, cn[cur], t, nn, pair_mode); CKLB("k_ploc_nn");
             k_ploc_flags<<<cdiv(m, 256), 256, 0, st>>>(m, nn, flags); CKLB("k_ploc_flags");
             uint32_t nb = cdiv(m, SCAN_TILE);
             k_scan_reduce<<<nb, SCAN_BLOCK, 0, st>>>(flags, m, bsums); CKLB("k_scan_reduce");
             k_scan_blocksums<<<1, 1024, 0, st>>>(bsums, nb, total); CKLB("k_scan_blocksums");
             k_scan_apply<<<nb, SCAN_BLOCK, 0, st>>>(flags, m, bsums, scan); CKLB("k_scan_apply");
-            k_ploc_merge<<<cdiv(m, 256), 256, 0, st>>>(m, n, created, nn, flags, scan, cs[cur], cn[cur], cs[cur ^ 1], cn[cur ^ 1], t);
+            k_ploc_merge<<<cdiv(m, 256), 256, 0, st>>>(m, n, created, nn, flags, scan, cn[cur], cn[cur ^ 1], t);
             CKLB("k_ploc_merge");
             uint64_t h_total = 0;
             CKB(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, st));
@@ -245,6 +249,10 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
 
     HNode *nodes;
     CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
+    if (n > 1) {
+        k_slot_to_tri<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_offset, slot_tri); CKLB("k_slot_to_tri");
+        k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit");
+    }
     if (kept_nodes > 0) {
         k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes); CKLB("k_emit_nodes");
         sc->d.root = 0;
@@ -326,6 +334,11 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     CKS(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CKS(cudaEventCreate(&sc->ev0)); CKS(cudaEventCreate(&sc->ev1));
     CKS(cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+        int per_sm = 0;
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false>, RT_TRACE_BLOCK, 0));
+        sc->trace_grid = sc->sm_count * std::max(1, per_sm);
+    }
     cudaStream_t st = sc->stream;
 
     // ---- tie-break ranks: the reference's leaf encounter order (raytracer.cpp:168-172, 208-209) ----
@@ -454,7 +467,7 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
 static uint32_t pool_limit() {
     const char *e = getenv("RT_B200_POOL");
     uint32_t v = e ? (uint32_t)strtoul(e, nullptr, 10) : 0;
-    return v ? v : (1u << 22);
+    return v ? v : (1u << 25);
 }
 
 static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
@@ -475,6 +488,8 @@ static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
     CK(p.mem.alloc(&p.hits, c));
     CK(p.mem.alloc(&p.shadow.q.o, c * lights)); CK(p.mem.alloc(&p.shadow.q.d, c * lights)); CK(p.mem.alloc(&p.shadow.rad, c * lights));
     CK(p.mem.alloc(&p.counts, 2 + lights)); CK(p.mem.alloc(&p.totals, 1)); CK(p.mem.alloc(&p.tcount, 1));
+    CK(p.mem.alloc(&p.acc_extra, c * (lights - 1))); CK(p.mem.alloc(&p.next, 1));
+    CK(cudaMemsetAsync(p.acc_extra, 0, std::max<size_t>(1, c * (lights - 1)) * sizeof(float4), sc->stream));
     p.shadow.count = p.counts + 2;
     p.shadow.capacity = capacity;
     if (p.h_counts) { cudaFreeHost(p.h_counts); p.h_counts = nullptr; }
@@ -540,44 +555,72 @@ static int collect_wave_times(rt_scene *sc) {
     return RT_OK;
 }
 
+static uint32_t fetch_min_knob() {
+    static uint32_t v = 0;
+    if (!v) { const char *e = getenv("RT_B200_FETCH_MIN"); v = e ? (uint32_t)atoi(e) : RT_FETCH_MIN; if (v < 1 || v > 32) v = RT_FETCH_MIN; }
+    return v;
+}
+
+static WaveQueues wave_queues(rt_scene *sc, int cur, uint32_t n_closest_max) {
+    Pool &p = sc->pool;
+    WaveQueues w;
+    w.closest = p.q[cur]; w.n_closest = p.counts + cur; w.closest_max = n_closest_max; w.hits = p.hits;
+    w.shadow = p.shadow.q; w.rad = p.shadow.rad; w.n_shadow = p.shadow.count; w.shadow_stride = p.shadow.capacity;
+    w.n_lights = sc->n_lights; w.acc = p.paths.acc; w.acc_extra = p.acc_extra; w.next = p.next;
+    w.fetch_min = fetch_min_knob();
+    return w;
+}
+
+static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, uint64_t work_bound, bool count, TraceCounters *tc) {
+    cudaStream_t st = sc->stream;
+    CK(cudaMemsetAsync(w.next, 0, 4, st));
+    uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sc->trace_grid, std::max<uint64_t>(1, (work_bound + RT_TRACE_BLOCK - 1) / RT_TRACE_BLOCK));
+    if (count) k_trace_wave<true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, tc);
+    else k_trace_wave<false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, tc);
+    CKL("k_trace_wave");
+    return RT_OK;
+}
+
+// Runs every live path of the pool to completion. Wave w: ONE trace launch (the pending nodes' closest-hit rays +
+// the shadow rays the previous shading step queued), then the shading / bounce-generation step.
 static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint32_t flags, uint64_t *launches) {
     const bool timed = (flags & RT_FLAG_TIME_KERNELS) != 0;
     Pool &p = sc->pool;
     cudaStream_t st = sc->stream;
     const bool count = (flags & RT_FLAG_COUNTERS) != 0;
     const uint32_t L = sc->n_lights;
-    const uint32_t max_grid = (uint32_t)sc->sm_count * 16u;
-    uint32_t n = n_first;
+    uint32_t n = n_first;            // closest-hit rays of this wave
+    uint64_t n_sh = 0;               // shadow rays of this wave
     int cur = 0;
-    while (n > 0) {
+    if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
+    while (n > 0 || n_sh > 0) {
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
+        { int rc_ = launch_trace_wave(sc, prm.ray_bias, wave_queues(sc, cur, n), (uint64_t)n + n_sh, count, p.tcount); if (rc_) return rc_; }
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
         if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
-        uint32_t grid = std::min(cdiv(n, 128), max_grid);
-        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
-        if (count) k_trace_closest<true><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[cur], p.counts + cur, n, p.hits, p.tcount);
-        else k_trace_closest<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[cur], p.counts + cur, n, p.hits, p.tcount);
-        CKL("k_trace_closest");
-        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
-        k_logic<<<cdiv(n, 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, n, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
-        CKL("k_logic");
-        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
-        CK(cudaMemcpyAsync(p.h_counts, p.counts, 4 * (2 + L), cudaMemcpyDeviceToHost, st));
-        for (uint32_t l = 0; l < L; ++l) {        // at most n shadow rays per light; the kernel reads the real count on the device
-            RayQueue sq; sq.o = p.shadow.q.o + (size_t)l * p.shadow.capacity; sq.d = p.shadow.q.d + (size_t)l * p.shadow.capacity;
-            const float4 *rad = p.shadow.rad + (size_t)l * p.shadow.capacity;
-            if (count) k_trace_shadow<true><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, sq, rad, p.shadow.count + l, n, p.paths.acc, p.tcount);
-            else k_trace_shadow<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, sq, rad, p.shadow.count + l, n, p.paths.acc, p.tcount);
-            CKL("k_trace_shadow");
+        if (n > 0) {
+            k_logic<<<cdiv(n, 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, n, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
+            CKL("k_logic");
             *launches += 1;
         }
-        *launches += 2;
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
+        { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
+        CK(cudaMemcpyAsync(p.h_counts, p.counts, 4 * (2 + L), cudaMemcpyDeviceToHost, st));
+        *launches += 1;
         CK(cudaStreamSynchronize(st));
         sc->stats.closest_rays += n;
-        for (uint32_t l = 0; l < L; ++l) sc->stats.shadow_rays += p.h_counts[2 + l];
+        sc->stats.shadow_rays += n_sh;
         sc->stats.waves += 1;
         n = p.h_counts[cur ^ 1];
+        n_sh = 0;
+        for (uint32_t l = 0; l < L; ++l) n_sh += p.h_counts[2 + l];
         cur ^= 1;
+    }
+    if (L > 1) {
+        k_fold_light_acc<<<cdiv(n_first, 256), 256, 0, st>>>(p.paths.acc, p.acc_extra, n_first, p.shadow.capacity, L - 1);
+        CKL("k_fold_light_acc");
+        *launches += 1;
     }
     return RT_OK;
 }
@@ -712,38 +755,50 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params 
 // ---------------------------------------------------------------------------------------------
 // rt_trace_rays / rt_trace_primary / rt_trace_color
 // ---------------------------------------------------------------------------------------------
-extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray *rays, uint64_t n, int any_hit, rt_hit *out_hits,
+extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray *rays, uint64_t n, int mode, rt_hit *out_hits,
                              rt_counters *out_counters) {
     g_err.clear();
     if (!sc || !params || (n && (!rays || !out_hits))) return fail(RT_ERR_ARG, "null argument");
+    if (mode != RT_TRACE_CLOSEST && mode != RT_TRACE_ANY && mode != RT_TRACE_BRUTE) return fail(RT_ERR_ARG, "unknown trace mode %d", mode);
     CK(cudaSetDevice(sc->device));
     cudaStream_t st = sc->stream;
     memset(&sc->stats, 0, sizeof(sc->stats));
-    unsigned long long tot_s = 0, tot_c = 0;
     const uint32_t chunk = 1u << 20;
     DevArena tmp;
     auto done = [&](int r) { tmp.release(); return r; };
 #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
-    float *d_rays; RayQueue q; HitRec *hits; ApiHit *api; TraceCounters *tc;
+    float *d_rays; RayQueue q; HitRec *hits; ApiHit *api; TraceCounters *tc; float4 *rad, *acc; uint32_t *cnt;
     uint32_t cap = (uint32_t)std::min<uint64_t>(n ? n : 1, chunk);
     CKR(tmp.alloc(&d_rays, 6 * (size_t)cap)); CKR(tmp.alloc(&q.o, cap)); CKR(tmp.alloc(&q.d, cap)); CKR(tmp.alloc(&hits, cap));
-    CKR(tmp.alloc(&api, cap)); CKR(tmp.alloc(&tc, 1));
+    CKR(tmp.alloc(&api, cap)); CKR(tmp.alloc(&tc, 1)); CKR(tmp.alloc(&rad, cap)); CKR(tmp.alloc(&acc, cap)); CKR(tmp.alloc(&cnt, 4));
     CKR(cudaMemsetAsync(tc, 0, sizeof(TraceCounters), st));
     CKR(cudaEventRecord(sc->ev0, st));
     for (uint64_t b = 0; b < n; b += chunk) {
         uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - b);
         CKR(cudaMemcpyAsync(d_rays, rays + b, (size_t)m * sizeof(rt_ray), cudaMemcpyHostToDevice, st));
-        k_upload_rays<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q);
-        uint32_t grid = std::min(cdiv(m, 128), (uint32_t)sc->sm_count * 16u);
-        if (any_hit == RT_TRACE_ANY) k_trace_any<<<grid, 128, 0, st>>>(sc->d, params->ray_bias, q, m, hits);
-        else if (any_hit == RT_TRACE_BRUTE) k_trace_brute<<<cdiv(m, 128), 128, 0, st>>>(sc->d, params->ray_bias, q, m, hits);
-        else k_trace_closest<true><<<grid, 128, 0, st>>>(sc->d, params->ray_bias, q, nullptr, m, hits, tc);
-        k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, params->ray_bias, q, hits, m, api);
+        WaveQueues w;
+        memset(&w, 0, sizeof(w));
+        w.next = cnt + 1; w.hits = hits; w.acc = acc; w.acc_extra = acc; w.rad = rad; w.shadow = q; w.closest = q;
+        w.n_shadow = cnt; w.shadow_stride = cap; w.fetch_min = fetch_min_knob();
+        int rc = RT_OK;
+        if (mode == RT_TRACE_ANY) {
+            k_rays_to_shadow_queue<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q, rad, acc, cnt);
+            w.closest_max = 0; w.n_lights = 1;
+            rc = launch_trace_wave(sc, params->ray_bias, w, m, true, tc);
+            k_occlusion_to_api<<<cdiv(m, 256), 256, 0, st>>>(acc, m, api);
+        } else {
+            k_upload_rays<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q);
+            w.closest_max = m; w.n_lights = 0;
+            if (mode == RT_TRACE_BRUTE) k_trace_brute<<<cdiv(m, 128), 128, 0, st>>>(sc->d, params->ray_bias, q, m, hits);
+            else rc = launch_trace_wave(sc, params->ray_bias, w, m, true, tc);
+            k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, params->ray_bias, q, hits, m, api);
+        }
+        if (rc) return done(rc);
         { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "trace launch failed: %s", cudaGetErrorString(e_))); }
         CKR(cudaMemcpyAsync(out_hits + b, api, (size_t)m * sizeof(ApiHit), cudaMemcpyDeviceToHost, st));
         CKR(cudaStreamSynchronize(st));
         sc->stats.kernel_launches += 3;
-        sc->stats.closest_rays += m;
+        if (mode == RT_TRACE_ANY) sc->stats.shadow_rays += m; else sc->stats.closest_rays += m;
     }
     CKR(cudaEventRecord(sc->ev1, st));
     TraceCounters htc;
@@ -751,8 +806,7 @@ extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray
     CKR(cudaStreamSynchronize(st));
     float ms = 0; CKR(cudaEventElapsedTime(&ms, sc->ev0, sc->ev1));
     sc->stats.gpu_ms = ms;
-    tot_s = htc.sphere_checks; tot_c = htc.cluster_checks;
-    if (out_counters) { out_counters->ray_count = n; out_counters->sphere_check_count = tot_s; out_counters->mesh_check_count = tot_c; }
+    if (out_counters) { out_counters->ray_count = n; out_counters->sphere_check_count = htc.sphere_checks; out_counters->mesh_check_count = htc.cluster_checks; }
     return done(RT_OK);
 #undef CKR
 }
@@ -795,8 +849,10 @@ extern "C" int rt_trace_primary(rt_scene *sc, const rt_camera *cam, const rt_par
             const uint32_t m = npix * ns;
             k_raygen<<<cdiv(m, 256), 256, 0, st>>>(dcam, prm, p.paths, p.q[0], m, ns, width, d_ids, pixel_begin, p0, sample_begin + s0, 0.5f, p.counts);
             if (out_hits) {
-                uint32_t grid = std::min(cdiv(m, 128), (uint32_t)sc->sm_count * 16u);
-                k_trace_closest<false><<<grid, 128, 0, st>>>(sc->d, prm.ray_bias, p.q[0], nullptr, m, p.hits, p.tcount);
+                WaveQueues w = wave_queues(sc, 0, m);
+                w.n_closest = nullptr; w.n_lights = 0;
+                rc = launch_trace_wave(sc, prm.ray_bias, w, m, false, p.tcount);
+                if (rc) return done(rc);
                 k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, prm.ray_bias, p.q[0], p.hits, m, api);
                 sc->stats.kernel_launches += 2; sc->stats.closest_rays += m;
             }

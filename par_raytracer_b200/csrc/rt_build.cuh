@@ -18,7 +18,9 @@
 #ifndef RT_LEAF_MAX
 #define RT_LEAF_MAX 4
 #endif
+#ifndef PLOC_RADIUS
 #define PLOC_RADIUS 16
+#endif
 
 // ---- small utilities -----------------------------------------------------------------------
 
@@ -78,7 +80,7 @@ struct BuildInput {
 
 RT_DEVICE f3 ld3(const float *p, uint32_t i) { return mk3(p[3 * (size_t)i], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]); }
 
-__global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, uint32_t *bounds /*6 flipped floats*/) {
+__global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, float4 *tri_lo, float4 *tri_hi, uint32_t *bounds /*6 flipped floats*/) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     f3 lo = mk3(FLT_MAX, FLT_MAX, FLT_MAX), hi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
     if (j < in.n_tris) {
@@ -107,6 +109,8 @@ __global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, uint32_t *bound
         if (!(r2 < FLT_MAX)) { ctr = (a + b + c) * (1.0f / 3.0f); da = a - ctr; db = b - ctr; dc = c - ctr;
                                 r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc))); }
         tri_sphere[j] = make_float4(ctr.x, ctr.y, ctr.z, sqrtf(r2) * 1.000002f + 1e-30f);
+        tri_lo[j] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.0f);
+        tri_hi[j] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.0f);
         lo = ctr; hi = ctr;
     }
     // block reduce of centre bounds
@@ -248,36 +252,43 @@ struct TempTree {           // 2n - 1 nodes: [0, n) = sorted triangles, [n, 2n-1
     uint32_t *size;          // triangles in subtree
     uint32_t *kept;          // internal nodes with size > RT_LEAF_MAX in subtree (incl. self)
     float4 *sphere;
+    float4 *lo, *hi;         // exact axis-aligned bounds of the subtree's vertices
 };
 
-__global__ void k_ploc_init(uint32_t n, const uint32_t *sorted_tri, const float4 *tri_sphere, float4 *cl_sphere, int32_t *cl_node,
-                            TempTree t) {
+__global__ void k_ploc_init(uint32_t n, const uint32_t *sorted_tri, const float4 *tri_sphere, const float4 *tri_lo, const float4 *tri_hi,
+                            int32_t *cl_node, TempTree t) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 s = tri_sphere[sorted_tri[i]];
-    cl_sphere[i] = s; cl_node[i] = (int32_t)i;
-    t.c0[i] = -1; t.c1[i] = -1; t.parent[i] = -1; t.size[i] = 1; t.kept[i] = 0; t.sphere[i] = s;
+    uint32_t j = sorted_tri[i];
+    cl_node[i] = (int32_t)i;
+    t.c0[i] = -1; t.c1[i] = -1; t.parent[i] = -1; t.size[i] = 1; t.kept[i] = 0; t.sphere[i] = tri_sphere[j];
+    t.lo[i] = tri_lo[j]; t.hi[i] = tri_hi[j];
 }
 
-__global__ void __launch_bounds__(256) k_ploc_nn(uint32_t m, const float4 *cl_sphere, uint32_t *nn, int pair_mode) {
-    __shared__ float4 sh[256 + 2 * PLOC_RADIUS];
+// Search cost = squared diagonal of the merged bounds, i.e. (2 x radius)^2 of the sphere around the merged box:
+// the reference's "smallest parent radius" criterion (bsphere.cpp:295-299) on exact extents instead of on spheres of spheres.
+__global__ void __launch_bounds__(256) k_ploc_nn(uint32_t m, const int32_t *cl_node, TempTree t, uint32_t *nn, int pair_mode) {
+    __shared__ float4 slo[256 + 2 * PLOC_RADIUS];
+    __shared__ float4 shi[256 + 2 * PLOC_RADIUS];
     int base = (int)(blockIdx.x * 256) - PLOC_RADIUS;
-    for (int t = threadIdx.x; t < 256 + 2 * PLOC_RADIUS; t += 256) {
-        int g = base + t;
-        sh[t] = (g >= 0 && g < (int)m) ? cl_sphere[g] : make_float4(0, 0, 0, -1.0f);
+    for (int k = threadIdx.x; k < 256 + 2 * PLOC_RADIUS; k += 256) {
+        int g = base + k;
+        if (g >= 0 && g < (int)m) { int32_t nd = cl_node[g]; slo[k] = t.lo[nd]; shi[k] = t.hi[nd]; }
+        else { slo[k] = make_float4(0, 0, 0, -1.0f); shi[k] = slo[k]; }
     }
     __syncthreads();
     uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= m) return;
     if (pair_mode) { uint32_t j = i ^ 1u; nn[i] = j < m ? j : i; return; }
-    float4 me = sh[threadIdx.x + PLOC_RADIUS];
+    float4 lo = slo[threadIdx.x + PLOC_RADIUS], hi = shi[threadIdx.x + PLOC_RADIUS];
     float best = FLT_MAX; uint32_t bj = i;
     for (int o = -PLOC_RADIUS; o <= PLOC_RADIUS; ++o) {
         if (o == 0) continue;
-        float4 other = sh[threadIdx.x + PLOC_RADIUS + o];
-        if (other.w < 0.0f) continue;
-        float r = enclose_radius(me, other);
-        if (r < best) { best = r; bj = (uint32_t)((int)i + o); }
+        float4 l2 = slo[threadIdx.x + PLOC_RADIUS + o], h2 = shi[threadIdx.x + PLOC_RADIUS + o];
+        if (l2.w < 0.0f) continue;
+        float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+        float c = dx * dx + dy * dy + dz * dz;
+        if (c < best) { best = c; bj = (uint32_t)((int)i + o); }
     }
     nn[i] = bj;
 }
@@ -294,7 +305,7 @@ __global__ void k_ploc_flags(uint32_t m, const uint32_t *nn, uint64_t *flags) {
 }
 
 __global__ void k_ploc_merge(uint32_t m, uint32_t n, uint32_t nodes_created, const uint32_t *nn, const uint64_t *flags, const uint64_t *scan,
-                             const float4 *cl_sphere, const int32_t *cl_node, float4 *out_sphere, int32_t *out_node, TempTree t) {
+                             const int32_t *cl_node, int32_t *out_node, TempTree t) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     uint64_t f = flags[i];
@@ -305,15 +316,17 @@ __global__ void k_ploc_merge(uint32_t m, uint32_t n, uint32_t nodes_created, con
         uint32_t j = nn[i];
         int32_t a = cl_node[i], b = cl_node[j];
         int32_t id = (int32_t)(n + nodes_created + (uint32_t)(sc >> 32));
-        float4 s = enclose_spheres(cl_sphere[i], cl_sphere[j]);
         t.c0[id] = a; t.c1[id] = b; t.parent[id] = -1; t.parent[a] = id; t.parent[b] = id;
         uint32_t sz = t.size[a] + t.size[b];
         t.size[id] = sz;
         t.kept[id] = sz > RT_LEAF_MAX ? 1u + t.kept[a] + t.kept[b] : 0u;
-        t.sphere[id] = s;
-        out_sphere[pos] = s; out_node[pos] = id;
+        t.sphere[id] = enclose_spheres(t.sphere[a], t.sphere[b]);
+        float4 la = t.lo[a], lb = t.lo[b], ha = t.hi[a], hb = t.hi[b];
+        t.lo[id] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+        t.hi[id] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+        out_node[pos] = id;
     } else {
-        out_sphere[pos] = cl_sphere[i]; out_node[pos] = cl_node[i];
+        out_node[pos] = cl_node[i];
     }
 }
 
@@ -336,6 +349,38 @@ __global__ void k_layout(uint32_t n_nodes_total, TempTree t, uint32_t *tri_offse
     tri_offset[v] = off;
     kept_index[v] = idx;
     if (t.size[v] > RT_LEAF_MAX) atomicMax(max_depth, depth + 1);
+}
+
+// cluster-order slot -> input triangle
+__global__ void k_slot_to_tri(uint32_t n, const uint32_t *sorted_tri, const uint32_t *tri_offset, uint32_t *slot_tri) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot_tri[tri_offset[i]] = sorted_tri[i];
+}
+
+// Tight refit: a sphere of spheres of spheres ... grows with every level. Each internal node therefore also gets the
+// sphere centred on its box with the exact largest vertex distance as radius (one warp scans the node's contiguous
+// triangle range); the smaller of the two survives. Both enclose every vertex of the subtree.
+__global__ void __launch_bounds__(256) k_refit(uint32_t n, uint32_t n_total, TempTree t, const uint32_t *tri_offset, const uint32_t *slot_tri,
+                                               BuildInput in) {
+    uint32_t v = n + (blockIdx.x * blockDim.x + threadIdx.x) / 32u;
+    uint32_t lane = threadIdx.x & 31u;
+    if (v >= n_total) return;
+    float4 lo = t.lo[v], hi = t.hi[v];
+    f3 ctr = mk3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
+    uint32_t off = tri_offset[v], size = t.size[v];
+    float d2 = 0.0f;
+    for (uint32_t k = lane; k < size; k += 32u) {
+        uint32_t j = slot_tri[off + k];
+        for (int c = 0; c < 3; ++c) {
+            f3 p = ld3(in.positions, in.idx_positions[3 * (size_t)j + c]) - ctr;
+            d2 = fmaxf(d2, dot3(p, p));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if (lane == 0) {
+        float r = sqrtf(d2) * 1.000002f + 1e-30f;
+        if (r < t.sphere[v].w) t.sphere[v] = make_float4(ctr.x, ctr.y, ctr.z, r);
+    }
 }
 
 __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, const uint32_t *tri_offset, const uint32_t *kept_index,

@@ -438,3 +438,39 @@ __global__ void k_rng_kat(uint64_t seed, uint32_t n, uint64_t *out) {
     rng_seed(r, seed);
     for (uint32_t i = 0; i < n; ++i) out[i] = rng_next(r);
 }
+
+// lights >= 1 accumulate into their own per-path buffers (single writer, no atomics); fold them into the path
+// accumulator in light order once every wave of the batch has finished
+__global__ void k_fold_light_acc(float4 *acc, float4 *acc_extra, uint32_t n, uint32_t stride, uint32_t n_extra) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float4 a = acc[s];
+    for (uint32_t l = 0; l < n_extra; ++l) {
+        float4 e = acc_extra[(size_t)l * stride + s];
+        a.x += e.x; a.y += e.y; a.z += e.z;
+        acc_extra[(size_t)l * stride + s] = make_float4(0, 0, 0, 0);
+    }
+    acc[s] = a;
+}
+
+// rt_trace_rays(RT_TRACE_ANY): rays go through the SHADOW path of the wave kernel with radiance (1, 0, 0); a path
+// accumulator that stayed 0 means "occluded" == TraceRay returned true
+__global__ void k_rays_to_shadow_queue(const float *rays, uint32_t n, RayQueue q, float4 *rad, float4 *acc, uint32_t *count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count = n;
+    if (i >= n) return;
+    const float *rp = rays + 6 * (size_t)i;
+    q.o[i] = make_float4(rp[0], rp[1], rp[2], __uint_as_float(i));
+    q.d[i] = make_float4(rp[3], rp[4], rp[5], -1.0f);
+    rad[i] = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    acc[i] = make_float4(0, 0, 0, 0);
+}
+__global__ void k_occlusion_to_api(const float4 *acc, uint32_t n, ApiHit *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ApiHit a;
+    memset(&a, 0, sizeof(a));
+    a.hit = acc[i].x == 0.0f ? 1u : 0u;
+    a.t = FLT_MAX; a.object = -1;
+    out[i] = a;
+}

@@ -84,126 +84,149 @@ RT_DEVICE bool tri_test(const TriRec &r, const RayCtx &c, float &t_out, float &v
     return true;
 }
 
-template <bool ANY_HIT, bool COUNT>
-RT_DEVICE void trace_one(const DevScene &S, float bias, f3 org, f3 dir, HitRec &best, uint32_t &best_rank,
-                         unsigned long long &n_sph, unsigned long long &n_clu) {
-    RayCtx c;
-    c.d = dir;
-    c.o = org + dir * bias;                              // raytracer.cpp:163
-    f3 q = c.o + dir;
-    c.qp = c.o - q;
-    float dd = __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x));
-    float inv_dd = 1.0f / dd;
-    best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1;   // raytracer.cpp:166
-    best_rank = 0xFFFFFFFFu;
-    if (S.n_tris == 0) return;
+// ---- the wave trace kernel -----------------------------------------------------------------------------
+// One launch traces everything a wave has to trace: the closest-hit rays of the pending recursion nodes AND the
+// shadow rays queued by the previous shading step (ShadeLight, raytracer.cpp:378-411), so a wave pays one
+// launch tail instead of two.
+//
+// Warp-cooperative scheduling: warps are persistent (grid = resident warps of the chip) and pull rays from one
+// global work counter. A lane whose ray has finished does not wait for the slowest lane of its warp: as soon as
+// RT_FETCH_MIN lanes are idle the warp fetches that many consecutive rays with ONE atomicAdd (consecutive
+// queue entries are spatially coherent: same pixel / neighbouring pixels). Traversal per lane is a short-stack
+// while-while loop: descend internal nodes nearest-child first, then scan the reached cluster.
+#define RT_TRACE_BLOCK 128
+#ifndef RT_FETCH_MIN
+#define RT_FETCH_MIN 12
+#endif
+
+struct WaveQueues {
+    RayQueue closest;              // d.w = path slot
+    const uint32_t *n_closest;     // device-side count (NULL: closest_max rays)
+    uint32_t closest_max;
+    HitRec *hits;
+    RayQueue shadow;               // light l owns [l * shadow_stride, ...): o.w = path slot, d.w = light_dist_sq or < 0
+    const float4 *rad;             // radiance to add when the light is visible
+    const uint32_t *n_shadow;      // [n_lights] device-side counts
+    uint32_t shadow_stride, n_lights;
+    float4 *acc;                   // light 0 adds into the path accumulator ...
+    float4 *acc_extra;             // ... light l >= 1 into acc_extra[(l - 1) * shadow_stride + slot] (single writer each: no atomics)
+    uint32_t *next;                // work counter, zero before launch
+    uint32_t fetch_min;            // refill the warp once this many lanes are idle (32 = only when all are)
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float bias, WaveQueues W, TraceCounters *counters) {
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nC = W.n_closest ? min(*W.n_closest, W.closest_max) : W.closest_max;
+    uint32_t total = nC;
+    for (uint32_t l = 0; l < W.n_lights; ++l) total += min(W.n_shadow[l], W.shadow_stride);
+    unsigned long long n_sph = 0, n_clu = 0;
+
+    bool live = false, exhausted = false;
+    RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
+    float inv_dd = 0.0f, dist_sq = -1.0f;
+    HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
+    uint32_t best_rank = 0xFFFFFFFFu, out_idx = 0, light = 0;
+    int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light)
+    int cur = 0, sp = 0;
     int stack[RT_STACK_MAX];
-    int sp = 0;
-    int cur = S.root;
+
     while (true) {
-        while (cur >= 0) {
-            const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
-            float4 s0 = __ldg(np), s1 = __ldg(np + 1);
-            int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 2));
-            float t0, t1;
-            // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
-            bool h0 = cull_sphere(s0, c.o, c.d, inv_dd, best.t, t0);
-            bool h1 = cull_sphere(s1, c.o, c.d, inv_dd, best.t, t1);
-            if (COUNT) n_sph += 2;
-            if (h0 && h1) {
-                int near = ch.x, far = ch.y;
-                if (t1 < t0) { near = ch.y; far = ch.x; }
-                if (sp < RT_STACK_MAX) stack[sp++] = far;
-                cur = near;
-            } else if (h0) cur = ch.x;
-            else if (h1) cur = ch.y;
-            else {
-                if (sp == 0) return;
-                cur = stack[--sp];
-            }
-        }
-        // cluster (leaf): linear scan like IntersectRayMesh (raytracer.cpp:136-154), <= RT_LEAF_MAX triangles
-        {
-            uint32_t first = leaf_first(cur), cnt = leaf_count(cur);
-            if (COUNT) n_clu += 1;
-            for (uint32_t k = 0; k < cnt; ++k) {
-                uint32_t ti = first + k;
-                const float4 *tp = reinterpret_cast<const float4 *>(S.tris + ti);
-                TriRec r; r.r0 = __ldg(tp); r.r1 = __ldg(tp + 1); r.r2 = __ldg(tp + 2);
-                float t, v, w;
-                if (tri_test(r, c, t, v, w)) {
-                    if (t <= best.t && t < FLT_MAX) {           // t < FLT_MAX: raytracer.cpp:149/220 against { FLT_MAX }
-                        uint32_t rk = __ldg(S.tri_rank + ti);
-                        if (t < best.t || rk < best_rank) { best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk; }
-                        if (ANY_HIT) return;
+        // ---- warp-cooperative fetch ----
+        uint32_t idle = __ballot_sync(FULL, !live);
+        if (!exhausted && (idle == FULL || __popc(idle) >= W.fetch_min)) {
+            uint32_t n_idle = __popc(idle), base = 0;
+            if (lane == 0) base = atomicAdd(W.next, n_idle);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + n_idle >= total) exhausted = true;
+            if (!live) {
+                uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < total) {
+                    float4 o4, d4;
+                    if (idx < nC) { o4 = W.closest.o[idx]; d4 = W.closest.d[idx]; kind = 0; out_idx = idx; }
+                    else {
+                        uint32_t j = idx - nC; light = 0;
+                        while (true) { uint32_t ns = min(W.n_shadow[light], W.shadow_stride); if (j < ns) break; j -= ns; light++; }
+                        size_t e = (size_t)light * W.shadow_stride + j;
+                        o4 = W.shadow.o[e]; d4 = W.shadow.d[e];
+                        dist_sq = d4.w; kind = d4.w < 0.0f ? 1 : 2; out_idx = (uint32_t)e;
                     }
+                    f3 dir = mk3(d4);
+                    c.d = dir;
+                    c.o = mk3(o4) + dir * bias;                      // raytracer.cpp:163
+                    f3 q = c.o + dir;
+                    c.qp = c.o - q;
+                    inv_dd = 1.0f / __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x));
+                    best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1; best_rank = 0xFFFFFFFFu;   // raytracer.cpp:166
+                    cur = S.root; sp = 0;
+                    live = true;
                 }
             }
         }
-        if (sp == 0) return;
-        cur = stack[--sp];
-    }
-}
+        if (__ballot_sync(FULL, live) == 0) break;
 
-// ---- closest hit over a ray queue ----------------------------------------------------------------------
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_closest(DevScene S, float bias, RayQueue q, const uint32_t *n_rays_ptr, uint32_t n_rays_max,
-                                                      HitRec *hits, TraceCounters *counters) {
-    uint32_t n = n_rays_ptr ? min(*n_rays_ptr, n_rays_max) : n_rays_max;
-    unsigned long long n_sph = 0, n_clu = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o = q.o[i], d = q.d[i];
-        HitRec h; uint32_t rk;
-        trace_one<false, COUNT>(S, bias, mk3(o), mk3(d), h, rk, n_sph, n_clu);
-        hits[i] = h;
+        if (live) {
+            bool done = S.n_tris == 0;
+            // ---- descend to the next cluster ----
+            while (!done && cur >= 0) {
+                const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
+                float4 s0 = __ldg(np), s1 = __ldg(np + 1);
+                int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 2));
+                float t0, t1;
+                // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
+                bool h0 = cull_sphere(s0, c.o, c.d, inv_dd, best.t, t0);
+                bool h1 = cull_sphere(s1, c.o, c.d, inv_dd, best.t, t1);
+                if (COUNT) n_sph += 2;
+                if (h0 && h1) {
+                    int near = ch.x, far = ch.y;
+                    if (t1 < t0) { near = ch.y; far = ch.x; }
+                    if (sp < RT_STACK_MAX) stack[sp++] = far;
+                    cur = near;
+                } else if (h0) cur = ch.x;
+                else if (h1) cur = ch.y;
+                else if (sp == 0) done = true;
+                else cur = stack[--sp];
+            }
+            // ---- cluster (leaf): linear scan like IntersectRayMesh (raytracer.cpp:136-154), <= RT_LEAF_MAX triangles ----
+            if (!done) {
+                uint32_t first = leaf_first(cur), cnt = leaf_count(cur);
+                if (COUNT) n_clu += 1;
+                for (uint32_t k = 0; k < cnt; ++k) {
+                    uint32_t ti = first + k;
+                    const float4 *tp = reinterpret_cast<const float4 *>(S.tris + ti);
+                    TriRec r; r.r0 = __ldg(tp); r.r1 = __ldg(tp + 1); r.r2 = __ldg(tp + 2);
+                    float t, v, w;
+                    if (tri_test(r, c, t, v, w) && t <= best.t && t < FLT_MAX) {    // t < FLT_MAX: raytracer.cpp:149/220 against { FLT_MAX }
+                        uint32_t rk = __ldg(S.tri_rank + ti);
+                        if (t < best.t || rk < best_rank) { best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk; }
+                    }
+                }
+                if (kind == 1 && best.tri >= 0) done = true;        // occlusion only needs TraceRay's bool (raytracer.cpp:385)
+                else if (sp == 0) done = true;
+                else cur = stack[--sp];
+            }
+            if (done) {
+                if (kind == 0) {
+                    W.hits[out_idx] = best;
+                } else {
+                    bool lit = best.tri < 0 || (kind == 2 && best.t * best.t <= dist_sq);   // raytracer.cpp:385 / 395-396
+                    if (lit) {
+                        uint32_t slot = __float_as_uint(W.shadow.o[out_idx].w);
+                        float4 r = W.rad[out_idx];
+                        float4 *dst = light == 0 ? W.acc + slot : W.acc_extra + (size_t)(light - 1) * W.shadow_stride + slot;
+                        float4 a = *dst;
+                        a.x += r.x; a.y += r.y; a.z += r.z;
+                        *dst = a;
+                    }
+                }
+                live = false;
+            }
+        }
     }
     if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) { n_sph += __shfl_down_sync(0xffffffffu, n_sph, o); n_clu += __shfl_down_sync(0xffffffffu, n_clu, o); }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&counters->sphere_checks, n_sph); atomicAdd(&counters->cluster_checks, n_clu); }
-    }
-}
-
-// ---- shadow rays (ShadeLight, raytracer.cpp:378-411) ---------------------------------------------------
-// o.w = slot bits, d.w = light_dist_sq for point lights (closest hit needed, raytracer.cpp:395-396) or < 0
-// for directional lights (boolean occlusion: TraceRay's return value, raytracer.cpp:385).
-// rad = radiance to add to the path's accumulator when the light is visible.
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_shadow(DevScene S, float bias, RayQueue q, const float4 *rad, const uint32_t *n_rays_ptr,
-                                                     uint32_t n_rays_max, float4 *acc, TraceCounters *counters) {
-    uint32_t n = n_rays_ptr ? min(*n_rays_ptr, n_rays_max) : n_rays_max;
-    unsigned long long n_sph = 0, n_clu = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 o = q.o[i], d = q.d[i];
-        HitRec h; uint32_t rk;
-        bool lit;
-        if (d.w < 0.0f) {
-            trace_one<true, COUNT>(S, bias, mk3(o), mk3(d), h, rk, n_sph, n_clu);
-            lit = h.tri < 0;
-        } else {
-            trace_one<false, COUNT>(S, bias, mk3(o), mk3(d), h, rk, n_sph, n_clu);
-            lit = h.tri < 0 || h.t * h.t <= d.w;
-        }
-        if (lit) {
-            uint32_t slot = __float_as_uint(o.w);
-            float4 r = rad[i];
-            float4 a = acc[slot];                       // one ray per path per launch: plain read-modify-write
-            a.x += r.x; a.y += r.y; a.z += r.z;
-            acc[slot] = a;
-        }
-    }
-    if (COUNT) {
-        for (int o = 16; o > 0; o >>= 1) { n_sph += __shfl_down_sync(0xffffffffu, n_sph, o); n_clu += __shfl_down_sync(0xffffffffu, n_clu, o); }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&counters->sphere_checks, n_sph); atomicAdd(&counters->cluster_checks, n_clu); }
-    }
-}
-
-// boolean occlusion for the API (rt_trace_rays, RT_TRACE_ANY): tri >= 0 <=> TraceRay would return true
-__global__ void __launch_bounds__(128) k_trace_any(DevScene S, float bias, RayQueue q, uint32_t n, HitRec *hits) {
-    unsigned long long a = 0, b = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        HitRec h; uint32_t rk;
-        trace_one<true, false>(S, bias, mk3(q.o[i]), mk3(q.d[i]), h, rk, a, b);
-        hits[i] = h;
+        for (int o = 16; o > 0; o >>= 1) { n_sph += __shfl_down_sync(FULL, n_sph, o); n_clu += __shfl_down_sync(FULL, n_clu, o); }
+        if (lane == 0) { atomicAdd(&counters->sphere_checks, n_sph); atomicAdd(&counters->cluster_checks, n_clu); }
     }
 }
 
