@@ -480,13 +480,13 @@ static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
     capacity = std::max(capacity, p.capacity); depth = std::max(depth, p.depth);
     p.capacity = p.depth = 0;
     size_t c = capacity;
-    CK(p.mem.alloc(&p.paths.rng_cur, c)); CK(p.mem.alloc(&p.paths.rng_x, c)); CK(p.mem.alloc(&p.paths.rng_seed, c));
-    CK(p.mem.alloc(&p.paths.rng_n, c)); CK(p.mem.alloc(&p.paths.acc, c)); CK(p.mem.alloc(&p.paths.node_T, c));
-    CK(p.mem.alloc(&p.paths.sp, c)); CK(p.mem.alloc(&p.paths.frames, c * RT_FRAME_F4 * depth));
+    CK(p.mem.alloc(&p.paths.rng_cx, c)); CK(p.mem.alloc(&p.paths.rng_seed, c));
+    CK(p.mem.alloc(&p.paths.acc, c)); CK(p.mem.alloc(&p.paths.node_T, c));
+    CK(p.mem.alloc(&p.paths.frames, c * RT_FRAME_F4 * depth));
     p.paths.capacity = capacity;
     for (int k = 0; k < 2; ++k) { CK(p.mem.alloc(&p.q[k].o, c)); CK(p.mem.alloc(&p.q[k].d, c)); }
     CK(p.mem.alloc(&p.hits, c));
-    CK(p.mem.alloc(&p.shadow.q.o, c * lights)); CK(p.mem.alloc(&p.shadow.q.d, c * lights)); CK(p.mem.alloc(&p.shadow.rad, c * lights));
+    CK(p.mem.alloc(&p.shadow.o, c * lights)); CK(p.mem.alloc(&p.shadow.rad, c * lights));
     CK(p.mem.alloc(&p.counts, 2 + lights)); CK(p.mem.alloc(&p.totals, 1)); CK(p.mem.alloc(&p.tcount, 1));
     CK(p.mem.alloc(&p.acc_extra, c * (lights - 1))); CK(p.mem.alloc(&p.next, 1));
     CK(cudaMemsetAsync(p.acc_extra, 0, std::max<size_t>(1, c * (lights - 1)) * sizeof(float4), sc->stream));
@@ -565,7 +565,7 @@ static WaveQueues wave_queues(rt_scene *sc, int cur, uint32_t n_closest_max) {
     Pool &p = sc->pool;
     WaveQueues w;
     w.closest = p.q[cur]; w.n_closest = p.counts + cur; w.closest_max = n_closest_max; w.hits = p.hits;
-    w.shadow = p.shadow.q; w.rad = p.shadow.rad; w.n_shadow = p.shadow.count; w.shadow_stride = p.shadow.capacity;
+    w.shadow_o = p.shadow.o; w.shadow_dir = nullptr; w.rad = p.shadow.rad; w.n_shadow = p.shadow.count; w.shadow_stride = p.shadow.capacity;
     w.n_lights = sc->n_lights; w.acc = p.paths.acc; w.acc_extra = p.acc_extra; w.next = p.next;
     w.fetch_min = fetch_min_knob();
     return w;
@@ -778,11 +778,11 @@ extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray
         CKR(cudaMemcpyAsync(d_rays, rays + b, (size_t)m * sizeof(rt_ray), cudaMemcpyHostToDevice, st));
         WaveQueues w;
         memset(&w, 0, sizeof(w));
-        w.next = cnt + 1; w.hits = hits; w.acc = acc; w.acc_extra = acc; w.rad = rad; w.shadow = q; w.closest = q;
+        w.next = cnt + 1; w.hits = hits; w.acc = acc; w.acc_extra = acc; w.rad = rad; w.shadow_o = q.o; w.shadow_dir = q.d; w.closest = q;
         w.n_shadow = cnt; w.shadow_stride = cap; w.fetch_min = fetch_min_knob();
         int rc = RT_OK;
         if (mode == RT_TRACE_ANY) {
-            k_rays_to_shadow_queue<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q, rad, acc, cnt);
+            k_rays_to_shadow_queue<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q.o, q.d, rad, acc, cnt);
             w.closest_max = 0; w.n_lights = 1;
             rc = launch_trace_wave(sc, params->ray_bias, w, m, true, tc);
             k_occlusion_to_api<<<cdiv(m, 256), 256, 0, st>>>(acc, m, api);

@@ -25,17 +25,22 @@
 #define RT_FRAME_F4 6            // float4 words per recursion frame
 
 struct PathPool {
-    uint64_t *rng_cur, *rng_x, *rng_seed;
-    uint32_t *rng_n;
+    uint4 *rng_cx;               // (cur.lo, cur.hi, x.lo, x.hi) of the 28-byte generator state (rt_rng.cuh)
+    uint64_t *rng_seed;          // only read on the rare > 15-draws replay path
     float4 *acc;                 // xyz: radiance gathered by the sample so far
-    float4 *node_T;              // xyz: throughput of the in-flight node, w: iters (int bits)
-    uint32_t *sp;                // live recursion frames
+    float4 *node_T;              // xyz: throughput of the in-flight node, w: iters | frames << 8 | draws << 16
     float4 *frames;              // [(level * RT_FRAME_F4 + k) * capacity + slot]
     uint32_t capacity;
 };
 
-RT_DEVICE void rng_load(const PathPool &P, uint32_t s, PathRng &r) { r.cur = P.rng_cur[s]; r.x = P.rng_x[s]; r.seed = P.rng_seed[s]; r.n = P.rng_n[s]; }
-RT_DEVICE void rng_store(const PathPool &P, uint32_t s, const PathRng &r) { P.rng_cur[s] = r.cur; P.rng_x[s] = r.x; P.rng_n[s] = r.n; }
+RT_DEVICE uint32_t pack_state(int iters, uint32_t sp, uint32_t draws) { return (uint32_t)iters | (sp << 8) | (draws << 16); }
+
+RT_DEVICE void rng_unpack(uint4 cx, uint32_t draws, PathRng &r) {
+    r.cur = (uint64_t)cx.x | ((uint64_t)cx.y << 32); r.x = (uint64_t)cx.z | ((uint64_t)cx.w << 32); r.n = draws; r.seed = 0;
+}
+RT_DEVICE uint4 rng_pack(const PathRng &r) {
+    return make_uint4((uint32_t)r.cur, (uint32_t)(r.cur >> 32), (uint32_t)r.x, (uint32_t)(r.x >> 32));
+}
 
 // One atomicAdd per warp; every lane of the warp must call it.
 RT_DEVICE uint32_t warp_push(uint32_t *counter, bool pred) {
@@ -82,10 +87,9 @@ __global__ void k_raygen(DevCamera cam, DevParams prm, PathPool P, RayQueue q, u
     q.o[s] = mk4(org, 0.0f);
     q.d[s] = mk4u(dir, s);
     P.rng_seed[s] = r.seed;
-    rng_store(P, s, r);
+    P.rng_cx[s] = rng_pack(r);
     P.acc[s] = make_float4(0, 0, 0, 0);
-    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)prm.bounce_depth));
-    P.sp[s] = 0;
+    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
     if (s == 0) *n_rays_out = n_slots;
 }
 
@@ -100,10 +104,9 @@ __global__ void k_paths_from_rays(DevParams prm, PathPool P, RayQueue q, uint32_
     PathRng r;
     rng_seed(r, seeds[s]);
     P.rng_seed[s] = r.seed;
-    rng_store(P, s, r);
+    P.rng_cx[s] = rng_pack(r);
     P.acc[s] = make_float4(0, 0, 0, 0);
-    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float((int)prm.bounce_depth));
-    P.sp[s] = 0;
+    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
     if (s == 0) *n_rays_out = n;
 }
 
@@ -162,13 +165,18 @@ RT_DEVICE float fresnel_amount(float ior_exit, float ior_enter, f3 normal, f3 in
     float x3 = x * x2;
     return r0 + (1.0f - r0) * x2 * x3;
 }
-// powf(Max(0, spec_cos), Ns) (raytracer.cpp:388, 403). glibc's powf is not reproducible bit-for-bit on the GPU;
-// the double-precision pow rounded to float is within 1 ulp of it and only scales a colour (never control flow).
+// powf(Max(0, spec_cos), Ns) (raytracer.cpp:388, 403). glibc's powf cannot be reproduced bit-for-bit on the GPU; CUDA's
+// powf is within a few ulp of it and the value only scales a colour (never control flow). -DRT_PHONG_POW_F64 switches to
+// the double-precision pow rounded to float (<= 1 ulp from glibc, ~4x the instructions).
+#ifdef RT_PHONG_POW_F64
 RT_DEVICE float phong_pow(float x, float e) { return (float)pow((double)x, (double)e); }
+#else
+RT_DEVICE float phong_pow(float x, float e) { return powf(x, e); }
+#endif
 
 // One sub-queue per light (light l owns entries [l * capacity, (l + 1) * capacity) and count[l]): a path has at most one
 // ray in each, so the occlusion kernel adds to the path's accumulator without atomics and in light order.
-struct ShadowQueue { RayQueue q; float4 *rad; uint32_t *count; uint32_t capacity; };
+struct ShadowQueue { float4 *o; float4 *rad; uint32_t *count; uint32_t capacity; };   // o: origin.xyz + slot; rad: radiance.xyz + light_dist_sq (< 0: directional)
 
 // ---- K4 + K6: the coroutine step --------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
@@ -186,21 +194,23 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
     bool emit = false;
     f3 e_org = mk3(0, 0, 0), e_dir = mk3(0, 0, 0), e_T = mk3(0, 0, 0);
     int e_iters = 0;
-
-    // shadow rays of this node (one per light), pushed after the divergent part
     bool shade_hit = false;
     f3 hit_p = mk3(0, 0, 0), N = mk3(0, 0, 0), V = mk3(0, 0, 0), Ta = mk3(0, 0, 0), kd = mk3(0, 0, 0), ks = mk3(0, 0, 0);
     float spec_int = 0.0f, w_diffuse = 0.0f;
 
     if (active) {
+        // every independent load of the path's state is issued before the first use
         float4 o4 = qin.o[i], d4 = qin.d[i];
-        slot = __float_as_uint(d4.w);
         HitRec h = hits[i];
+        slot = __float_as_uint(d4.w);
         float4 t4 = P.node_T[slot];
-        T = mk3(t4); iters = __float_as_int(t4.w);
-        acc = mk3(P.acc[slot]);
-        sp = P.sp[slot];
-        rng_load(P, slot, rng);
+        uint4 cx = P.rng_cx[slot];
+        float4 a4 = P.acc[slot];
+        uint32_t st = __float_as_uint(t4.w);
+        T = mk3(t4); iters = (int)(st & 0xFFu); sp = (st >> 8) & 0xFFu;
+        rng_unpack(cx, st >> 16, rng);
+        if (rng.n >= 15u) rng.seed = P.rng_seed[slot];
+        acc = mk3(a4);
         f3 org = mk3(o4); V = mk3(d4);
 
         if (h.tri < 0) {
@@ -208,11 +218,13 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
         } else {
             const float4 *tp = reinterpret_cast<const float4 *>(S.tris + h.tri);
             float4 r0 = __ldg(tp);
+            float4 ua = __ldg(S.tri_uv + 2 * (size_t)h.tri), ub = __ldg(S.tri_uv + 2 * (size_t)h.tri + 1);
+            const float4 *np = S.tri_nrm + 3 * (size_t)h.tri;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             f3 ob = org + V * prm.ray_bias;                                  // raytracer.cpp:163
             f3 position = ob + V * h.t;                                      // raytracer.cpp:121
             f3 gn = normalize3(mk3(r0.x, r0.y, r0.z));                        // raytracer.cpp:122
             hit_p = position + gn * prm.ray_bias;                            // raytracer.cpp:425
-            float4 ua = __ldg(S.tri_uv + 2 * (size_t)h.tri), ub = __ldg(S.tri_uv + 2 * (size_t)h.tri + 1);
             int mat_id = __float_as_int(ub.z);
             DevMaterial M = S.materials[mat_id];
             float bwy = h.v, bwz = h.w;
@@ -227,6 +239,7 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
             }
             if (restart) {
                 // tail call TraceRayColor(ray, iters): its Russian roulette runs again unless this is the root level
+                if (iters != bd && rng.n >= 15u && rng.seed == 0) rng.seed = P.rng_seed[slot];
                 if (!(iters != bd && rng_float01(rng) < 0.5f)) {
                     emit = true;
                     e_org = position + (V * prm.ray_bias) * 2.0f;            // raytracer.cpp:450
@@ -239,9 +252,8 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
                 if (M.tex_ambient >= 0) ambient = ambient * tex_sample(S, M.tex_ambient, u, v);      // raytracer.cpp:454-462
                 if (M.tex_diffuse >= 0) kd = kd * tex_sample(S, M.tex_diffuse, u, v);
                 if (M.tex_specular >= 0) ks = tex_sample(S, M.tex_specular, u, v);
-                const float4 *np = S.tri_nrm + 3 * (size_t)h.tri;
                 f3 n = mk3(0, 0, 0);                                          // raytracer.cpp:464-467
-                n = n + mk3(__ldg(np)) * bwx; n = n + mk3(__ldg(np + 1)) * bwy; n = n + mk3(__ldg(np + 2)) * bwz;
+                n = n + mk3(n0) * bwx; n = n + mk3(n1) * bwy; n = n + mk3(n2) * bwz;
                 N = normalize3(n);
                 if (M.tex_bump >= 0) {                                       // raytracer.cpp:468-502
                     const float4 *gp = S.tri_tan + 3 * (size_t)h.tri;
@@ -269,7 +281,6 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
                     // children exist: push this node's recursion frame
                     f3 Td = (Ta * kd) * w_diffuse;                           // raytracer.cpp:544
                     f3 Ts = Ta * ks;                                         // raytracer.cpp:545
-                    f3 co = position + (V * prm.ray_bias) * 2.0f;            // raytracer.cpp:549
                     f3 Tc = T * (1.0f - alpha);
                     uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u);   // child index 0 in bits 8..30
                     float4 *F = P.frames + (size_t)(sp * RT_FRAME_F4) * cap + slot;
@@ -278,13 +289,46 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
                     F[2 * (size_t)cap] = mk4(V, spec_int);
                     F[3 * (size_t)cap] = mk4(Td, Tc.x);
                     F[4 * (size_t)cap] = mk4(Ts, Tc.y);
-                    F[5 * (size_t)cap] = mk4(co, Tc.z);
+                    if (translucent) F[5 * (size_t)cap] = mk4(position + (V * prm.ray_bias) * 2.0f, Tc.z);   // raytracer.cpp:549
                     sp++;
                 }
                 // iters == 0: the translucent continuation has iters - 1 < 0 and returns black (raytracer.cpp:416)
             }
         }
+    }
 
+    // ShadeLight (raytracer.cpp:378-411): everything but the visibility test is evaluated here; the shadow ray carries the
+    // pre-weighted radiance. Its direction is a function of (light, origin) and is re-derived by the trace kernel.
+    for (uint32_t l = 0; l < S.n_lights; ++l) {
+        f3 rad = mk3(0, 0, 0);
+        float dist_sq = -1.0f;
+        if (shade_hit) {
+            DevLight L = S.lights[l];
+            f3 lc = mk3(L.color[0], L.color[1], L.color[2]);
+            f3 lv;
+            if (L.type == 0) {
+                lv = mk3(L.facing[0], L.facing[1], L.facing[2]) * -1.0f;     // raytracer.cpp:240
+            } else {
+                f3 lp = mk3(L.position[0], L.position[1], L.position[2]);
+                lv = normalize3(lp - hit_p);                                 // raytracer.cpp:243
+                f3 dv = lp - hit_p;
+                dist_sq = dot3(dv, dv);
+                float fd = (sqrtf(dist_sq) / L.falloff) + 1.0f;              // raytracer.cpp:398-399
+                lc = lc * (1.0f / (fd * fd));
+            }
+            float spec_cos = dot3(V * -1.0f, reflect3(lv, N));               // raytracer.cpp:386-388
+            f3 dd = (lc * 2.0f) * max0(dot3(N, lv));
+            f3 ds = lc * phong_pow(max0(spec_cos), spec_int);
+            rad = Ta * (((dd * kd) * w_diffuse) + ds * ks);                  // raytracer.cpp:544-545
+        }
+        uint32_t spos = warp_push(sh.count + l, shade_hit) + l * sh.capacity;
+        if (shade_hit) {
+            sh.o[spos] = mk4u(hit_p, slot);
+            sh.rad[spos] = mk4(rad, dist_sq);
+        }
+    }
+
+    if (active) {
         // walk the recursion forward to the next ray that has to be traced
         while (!emit && sp > 0) {
             float4 *F = P.frames + (size_t)((sp - 1) * RT_FRAME_F4) * cap + slot;
@@ -296,6 +340,7 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
             uint32_t rs = prm.reflection_samples, ss = prm.spec_samples;
             if (child >= rs + ss + (has_cont ? 1u : 0u)) { sp--; continue; }
             F[0].w = __uint_as_float((meta & 0x800000FFu) | ((child + 1u) << 8));
+            if (rng.n >= 14u && rng.seed == 0) rng.seed = P.rng_seed[slot];
             f3 fp = mk3(f0);
             float4 f1 = F[1 * (size_t)cap];
             f3 fn = mk3(f1);
@@ -318,47 +363,15 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
             if (rng_float01(rng) < 0.5f) continue;
             emit = true; e_org = c_org; e_dir = c_dir; e_T = c_T; e_iters = f_iters - 1;
         }
-
         P.acc[slot] = mk4(acc, 0.0f);
-        P.sp[slot] = sp;
-        rng_store(P, slot, rng);
-        if (emit) P.node_T[slot] = mk4(e_T, __int_as_float(e_iters));
+        P.rng_cx[slot] = rng_pack(rng);
+        f3 Tn = emit ? e_T : T;
+        P.node_T[slot] = mk4u(Tn, pack_state(emit ? e_iters : iters, sp, rng.n));
     }
 
     // K6: compaction -- the next wave's queue holds only rays that exist
     uint32_t pos = warp_push(n_out, emit);
     if (emit) { qout.o[pos] = mk4(e_org, 0.0f); qout.d[pos] = mk4u(e_dir, slot); }
-
-    // ShadeLight (raytracer.cpp:378-411): everything but the visibility test is evaluated here
-    for (uint32_t l = 0; l < S.n_lights; ++l) {
-        bool push = shade_hit;
-        f3 lv = mk3(0, 0, 0), rad = mk3(0, 0, 0);
-        float dist_sq = -1.0f;
-        if (push) {
-            DevLight L = S.lights[l];
-            f3 lc = mk3(L.color[0], L.color[1], L.color[2]);
-            if (L.type == 0) {
-                lv = mk3(L.facing[0], L.facing[1], L.facing[2]) * -1.0f;     // raytracer.cpp:240
-            } else {
-                f3 lp = mk3(L.position[0], L.position[1], L.position[2]);
-                lv = normalize3(lp - hit_p);                                 // raytracer.cpp:243
-                f3 dv = lp - hit_p;
-                dist_sq = dot3(dv, dv);
-                float fd = (sqrtf(dist_sq) / L.falloff) + 1.0f;              // raytracer.cpp:398-399
-                lc = lc * (1.0f / (fd * fd));
-            }
-            float spec_cos = dot3(V * -1.0f, reflect3(lv, N));               // raytracer.cpp:386-388
-            f3 dd = (lc * 2.0f) * max0(dot3(N, lv));
-            f3 ds = lc * phong_pow(max0(spec_cos), spec_int);
-            rad = Ta * (((dd * kd) * w_diffuse) + ds * ks);                  // raytracer.cpp:544-545
-        }
-        uint32_t spos = warp_push(sh.count + l, push) + l * sh.capacity;
-        if (push) {
-            sh.q.o[spos] = mk4u(hit_p, slot);
-            sh.q.d[spos] = mk4(lv, dist_sq);
-            sh.rad[spos] = mk4(rad, 0.0f);
-        }
-    }
 }
 
 // ---- K7: accumulate / resolve (main.cpp:242, 262-263) -----------------------------------------------
@@ -455,14 +468,14 @@ __global__ void k_fold_light_acc(float4 *acc, float4 *acc_extra, uint32_t n, uin
 
 // rt_trace_rays(RT_TRACE_ANY): rays go through the SHADOW path of the wave kernel with radiance (1, 0, 0); a path
 // accumulator that stayed 0 means "occluded" == TraceRay returned true
-__global__ void k_rays_to_shadow_queue(const float *rays, uint32_t n, RayQueue q, float4 *rad, float4 *acc, uint32_t *count) {
+__global__ void k_rays_to_shadow_queue(const float *rays, uint32_t n, float4 *o, float4 *dir, float4 *rad, float4 *acc, uint32_t *count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *count = n;
     if (i >= n) return;
     const float *rp = rays + 6 * (size_t)i;
-    q.o[i] = make_float4(rp[0], rp[1], rp[2], __uint_as_float(i));
-    q.d[i] = make_float4(rp[3], rp[4], rp[5], -1.0f);
-    rad[i] = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    o[i] = make_float4(rp[0], rp[1], rp[2], __uint_as_float(i));
+    dir[i] = make_float4(rp[3], rp[4], rp[5], 0.0f);          // explicit directions (API rays have no light)
+    rad[i] = make_float4(1.0f, 0.0f, 0.0f, -1.0f);
     acc[i] = make_float4(0, 0, 0, 0);
 }
 __global__ void k_occlusion_to_api(const float4 *acc, uint32_t n, ApiHit *out) {

@@ -96,7 +96,7 @@ RT_DEVICE bool tri_test(const TriRec &r, const RayCtx &c, float &t_out, float &v
 // while-while loop: descend internal nodes nearest-child first, then scan the reached cluster.
 #define RT_TRACE_BLOCK 128
 #ifndef RT_FETCH_MIN
-#define RT_FETCH_MIN 12
+#define RT_FETCH_MIN 16
 #endif
 
 struct WaveQueues {
@@ -104,8 +104,9 @@ struct WaveQueues {
     const uint32_t *n_closest;     // device-side count (NULL: closest_max rays)
     uint32_t closest_max;
     HitRec *hits;
-    RayQueue shadow;               // light l owns [l * shadow_stride, ...): o.w = path slot, d.w = light_dist_sq or < 0
-    const float4 *rad;             // radiance to add when the light is visible
+    const float4 *shadow_o;        // light l owns [l * shadow_stride, ...): origin.xyz, w = path slot
+    const float4 *shadow_dir;      // NULL: direction = f(light, origin) as GetShadowRayForLight (raytracer.cpp:234-250); else explicit
+    const float4 *rad;             // radiance to add when the light is visible; w = light_dist_sq (point light) or < 0
     const uint32_t *n_shadow;      // [n_lights] device-side counts
     uint32_t shadow_stride, n_lights;
     float4 *acc;                   // light 0 adds into the path accumulator ...
@@ -149,8 +150,15 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                         uint32_t j = idx - nC; light = 0;
                         while (true) { uint32_t ns = min(W.n_shadow[light], W.shadow_stride); if (j < ns) break; j -= ns; light++; }
                         size_t e = (size_t)light * W.shadow_stride + j;
-                        o4 = W.shadow.o[e]; d4 = W.shadow.d[e];
-                        dist_sq = d4.w; kind = d4.w < 0.0f ? 1 : 2; out_idx = (uint32_t)e;
+                        o4 = W.shadow_o[e];
+                        dist_sq = W.rad[e].w; kind = dist_sq < 0.0f ? 1 : 2; out_idx = (uint32_t)e;
+                        if (W.shadow_dir) d4 = W.shadow_dir[e];
+                        else {
+                            const DevLight &Lt = S.lights[light];
+                            f3 lv = Lt.type == 0 ? mk3(Lt.facing[0], Lt.facing[1], Lt.facing[2]) * -1.0f                       // raytracer.cpp:240
+                                                 : normalize3(mk3(Lt.position[0], Lt.position[1], Lt.position[2]) - mk3(o4));    // raytracer.cpp:243
+                            d4 = mk4(lv, 0.0f);
+                        }
                     }
                     f3 dir = mk3(d4);
                     c.d = dir;
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                 } else {
                     bool lit = best.tri < 0 || (kind == 2 && best.t * best.t <= dist_sq);   // raytracer.cpp:385 / 395-396
                     if (lit) {
-                        uint32_t slot = __float_as_uint(W.shadow.o[out_idx].w);
+                        uint32_t slot = __float_as_uint(W.shadow_o[out_idx].w);
                         float4 r = W.rad[out_idx];
                         float4 *dst = light == 0 ? W.acc + slot : W.acc_extra + (size_t)(light - 1) * W.shadow_stride + slot;
                         float4 a = *dst;
