@@ -54,47 +54,72 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), read through NVML from a
+    background thread (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a polling
+    nvidia-smi process was measured to slow the many-sync wave loop by ~40 ms per step, NVML reads do not)."""
 
-    def __init__(self, index: int):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index: int, interval_s: float = 0.1):
+        self.index, self.interval = index, interval_s
+        self.sm, self.mask, self.power = [], 0, []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.mode = os.environ.get("RT_BENCH_CLOCKS", "nvml")
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        # torch's device order follows CUDA_VISIBLE_DEVICES; NVML's does not
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.index
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.interval)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        bits = [0x8, 0x40, 0x20, 0x4]
+        self.max_sm = None
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm.append(float(out[0])); self.max_sm = float(out[1])
+                for k, b in enumerate(bits):
+                    if out[2 + k].strip().lower().startswith("active"):
+                        self.mask |= b
+            except Exception:
+                pass
+            self.stop_flag.wait(self.interval)
 
     def start(self):
-        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.max_sm = None
+        target = self._run_nvml if self.mode == "nvml" else self._run_smi
+        if self.mode == "off":
+            return
+        self.thread = threading.Thread(target=target, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=5)
+        reasons = sorted(n for b, n in self.REASONS.items() if self.mask & b)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm, "reasons": reasons,
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None, "source": self.mode}
 
 
 # -------------------------------------------------------------------------------------------------

@@ -83,7 +83,8 @@ struct Pool {                 // per-render working set, kept between calls and 
     uint32_t *next = nullptr;          // work counter of the wave trace kernel
     WaveTotals *totals = nullptr;
     TraceCounters *tcount = nullptr;
-    uint32_t *h_counts = nullptr;      // pinned mirror of counts
+    uint32_t *h_counts = nullptr;      // pinned ring of count read-backs
+    cudaEvent_t count_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct rt_scene {
@@ -294,6 +295,7 @@ extern "C" void rt_scene_destroy(rt_scene *sc) {
     if (sc->stream) cudaStreamSynchronize(sc->stream);
     sc->pool.mem.release();
     if (sc->pool.h_counts) cudaFreeHost(sc->pool.h_counts);
+    for (int k = 0; k < 4; ++k) if (sc->pool.count_ev[k]) cudaEventDestroy(sc->pool.count_ev[k]);
     sc->mem.release();
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
@@ -493,7 +495,8 @@ static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
     p.shadow.count = p.counts + 2;
     p.shadow.capacity = capacity;
     if (p.h_counts) { cudaFreeHost(p.h_counts); p.h_counts = nullptr; }
-    CK(cudaMallocHost((void **)&p.h_counts, (2 + lights) * sizeof(uint32_t)));
+    CK(cudaMallocHost((void **)&p.h_counts, 4 * (2 + lights) * sizeof(uint32_t)));
+    for (int k = 0; k < 4; ++k) if (!p.count_ev[k]) CK(cudaEventCreateWithFlags(&p.count_ev[k], cudaEventDisableTiming));
     p.capacity = capacity; p.depth = depth; p.lights = lights;
     return RT_OK;
 }
@@ -583,40 +586,58 @@ static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, uint
 
 // Runs every live path of the pool to completion. Wave w: ONE trace launch (the pending nodes' closest-hit rays +
 // the shadow rays the previous shading step queued), then the shading / bounce-generation step.
+//
+// The host never stalls the GPU: queue sizes live in device memory (kernels read them there), and wave w + 1 is
+// enqueued -- with launch bounds taken from the newest counts the host already has -- BEFORE the host waits for
+// wave w's 16-byte count read-back. The read-backs only decide when to stop and feed the statistics.
+#define RT_COUNT_RING 4
 static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint32_t flags, uint64_t *launches) {
     const bool timed = (flags & RT_FLAG_TIME_KERNELS) != 0;
     Pool &p = sc->pool;
     cudaStream_t st = sc->stream;
     const bool count = (flags & RT_FLAG_COUNTERS) != 0;
     const uint32_t L = sc->n_lights;
-    uint32_t n = n_first;            // closest-hit rays of this wave
-    uint64_t n_sh = 0;               // shadow rays of this wave
-    int cur = 0;
+    const uint32_t stride = 2 + L;                      // words per read-back slot
     if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
-    while (n > 0 || n_sh > 0) {
+
+    uint32_t bound = n_first;                           // upper bound of the closest-hit queue of the wave being issued
+    uint32_t in_closest[RT_COUNT_RING] = {0};           // what the host knew when it issued wave w (for the statistics)
+    auto issue = [&](uint32_t w) -> int {
+        const int cur = (int)(w & 1u);
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
-        { int rc_ = launch_trace_wave(sc, prm.ray_bias, wave_queues(sc, cur, n), (uint64_t)n + n_sh, count, p.tcount); if (rc_) return rc_; }
+        { int rc_ = launch_trace_wave(sc, prm.ray_bias, wave_queues(sc, cur, bound), (uint64_t)bound * (1 + L), count, p.tcount); if (rc_) return rc_; }
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
         if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
-        if (n > 0) {
-            k_logic<<<cdiv(n, 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, n, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
-            CKL("k_logic");
-            *launches += 1;
-        }
+        k_logic<<<cdiv(std::max(1u, bound), 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
+        CKL("k_logic");
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
-        CK(cudaMemcpyAsync(p.h_counts, p.counts, 4 * (2 + L), cudaMemcpyDeviceToHost, st));
-        *launches += 1;
-        CK(cudaStreamSynchronize(st));
-        sc->stats.closest_rays += n;
-        sc->stats.shadow_rays += n_sh;
+        CK(cudaMemcpyAsync(p.h_counts + (size_t)(w % RT_COUNT_RING) * stride, p.counts, 4 * stride, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(p.count_ev[w % RT_COUNT_RING], st));
+        *launches += 2;
+        return RT_OK;
+    };
+
+    uint64_t sh_in = 0;                                 // shadow rays traced by the wave whose read-back we wait for
+    uint32_t c_in = n_first;                            // closest rays traced by that wave
+    { int rc_ = issue(0); if (rc_) return rc_; }
+    for (uint32_t w = 0;; ++w) {
+        { int rc_ = issue(w + 1); if (rc_) return rc_; }                       // run ahead by one wave
+        CK(cudaEventSynchronize(p.count_ev[w % RT_COUNT_RING]));
+        const uint32_t *hc = p.h_counts + (size_t)(w % RT_COUNT_RING) * stride;
+        const int cur = (int)(w & 1u);
+        uint32_t c_out = hc[cur ^ 1];
+        uint64_t sh_out = 0;
+        for (uint32_t l = 0; l < L; ++l) sh_out += hc[2 + l];
+        sc->stats.closest_rays += c_in;
+        sc->stats.shadow_rays += sh_in;
         sc->stats.waves += 1;
-        n = p.h_counts[cur ^ 1];
-        n_sh = 0;
-        for (uint32_t l = 0; l < L; ++l) n_sh += p.h_counts[2 + l];
-        cur ^= 1;
+        c_in = c_out; sh_in = sh_out;
+        bound = c_out;                                  // queue sizes never grow: every live path emits at most one ray per wave
+        if (c_out == 0 && sh_out == 0) break;           // the wave already in flight finds empty queues and does nothing
     }
+    (void)in_closest;
     if (L > 1) {
         k_fold_light_acc<<<cdiv(n_first, 256), 256, 0, st>>>(p.paths.acc, p.acc_extra, n_first, p.shadow.capacity, L - 1);
         CKL("k_fold_light_acc");
