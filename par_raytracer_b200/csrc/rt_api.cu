@@ -271,6 +271,11 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     sc->d.nodes = nodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
     sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object;
     sc->d.n_tris = n; sc->d.n_nodes = kept_nodes;
+    {   // every sphere lies inside the root sphere: |c|_1 + r <= |c_root|_1 + sqrt(3) * 2 r_root + r_root
+        float4 rs;
+        CKB(cudaMemcpy(&rs, t.sphere + (n_total - 1), sizeof(rs), cudaMemcpyDeviceToHost));
+        sc->d.cull_bound = fabsf(rs.x) + fabsf(rs.y) + fabsf(rs.z) + 4.5f * rs.w;
+    }
     sc->info[0] = n; sc->info[1] = 0; sc->info[2] = kept_nodes; sc->info[3] = depth;
     sc->info[4] = (uint64_t)kept_nodes * sizeof(HNode); sc->info[5] = (uint64_t)n * sizeof(TriRec);
     sc->info[6] = (uint64_t)(ms * 1000.0f); sc->info[7] = iterations;

@@ -105,6 +105,7 @@ struct DevScene {
     const float4 *spec_dir;        // [(n_materials + 1) * spec_samples] Phong-lobe directions (raytracer.cpp:290-300)
     uint32_t n_tris, n_nodes, n_materials, n_lights;
     int32_t root;                  // 0, or a leaf ref when the scene has <= one cluster
+    float cull_bound;              // >= |c|_1 + r for every sphere of the hierarchy (see cull_sphere)
 };
 
 struct DevParams {

@@ -179,7 +179,10 @@ RT_DEVICE float phong_pow(float x, float e) { return powf(x, e); }
 struct ShadowQueue { float4 *o; float4 *rad; uint32_t *count; uint32_t capacity; };   // o: origin.xyz + slot; rad: radiance.xyz + light_dist_sq (< 0: directional)
 
 // ---- K4 + K6: the coroutine step --------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
+#ifndef RT_LOGIC_MIN_BLOCKS
+#define RT_LOGIC_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
                                               uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh) {
     uint32_t n_in = min(*n_in_ptr, n_in_max);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
     bool emit = false;
     f3 e_org = mk3(0, 0, 0), e_dir = mk3(0, 0, 0), e_T = mk3(0, 0, 0);
     int e_iters = 0;
-    bool shade_hit = false;
+    bool shade_hit = false, fresh_frame = false;      // fresh_frame: the top frame was pushed by this thread, its fields are still in registers
+    f3 f_Td = mk3(0, 0, 0);
     f3 hit_p = mk3(0, 0, 0), N = mk3(0, 0, 0), V = mk3(0, 0, 0), Ta = mk3(0, 0, 0), kd = mk3(0, 0, 0), ks = mk3(0, 0, 0);
     float spec_int = 0.0f, w_diffuse = 0.0f;
 
@@ -282,7 +286,8 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
                     f3 Td = (Ta * kd) * w_diffuse;                           // raytracer.cpp:544
                     f3 Ts = Ta * ks;                                         // raytracer.cpp:545
                     f3 Tc = T * (1.0f - alpha);
-                    uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u);   // child index 0 in bits 8..30
+                    fresh_frame = prm.reflection_samples > 0;
+                    uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u) | (fresh_frame ? (1u << 8) : 0u);   // next child index in bits 8..30
                     float4 *F = P.frames + (size_t)(sp * RT_FRAME_F4) * cap + slot;
                     F[0 * (size_t)cap] = mk4u(hit_p, meta);
                     F[1 * (size_t)cap] = mk4u(N, (uint32_t)mat_id);
@@ -291,6 +296,7 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
                     F[4 * (size_t)cap] = mk4(Ts, Tc.y);
                     if (translucent) F[5 * (size_t)cap] = mk4(position + (V * prm.ray_bias) * 2.0f, Tc.z);   // raytracer.cpp:549
                     sp++;
+                    f_Td = Td;
                 }
                 // iters == 0: the translucent continuation has iters - 1 < 0 and returns black (raytracer.cpp:416)
             }
@@ -330,6 +336,16 @@ __global__ void __launch_bounds__(128) k_logic(DevScene S, DevParams prm, PathPo
 
     if (active) {
         // walk the recursion forward to the next ray that has to be traced
+        if (fresh_frame) {
+            // first child of the node shaded above (a diffuse sample, raytracer.cpp:516-526): same arithmetic as the generic
+            // walk below, operands taken from registers instead of re-reading the frame just written (its child index
+            // was stored as 1 already)
+            if (rng.n >= 14u && rng.seed == 0) rng.seed = P.rng_seed[slot];
+            uint32_t series_i = (uint32_t)(rng_next(rng) % 1024ull);
+            f3 c_dir = to_world(N, mk3(__ldg(S.hamm_dir + series_i)));
+            f3 c_T = f_Td * max0(dot3(N, c_dir));
+            if (!(rng_float01(rng) < 0.5f)) { emit = true; e_org = hit_p; e_dir = c_dir; e_T = c_T; e_iters = iters - 1; }
+        }
         while (!emit && sp > 0) {
             float4 *F = P.frames + (size_t)((sp - 1) * RT_FRAME_F4) * cap + slot;
             float4 f0 = F[0];

@@ -32,26 +32,25 @@ struct HitRec {                // 16 B per ray
 
 struct TraceCounters { unsigned long long sphere_checks, cluster_checks; };
 
-RT_DEVICE float approx_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RT_DEVICE float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // culling only: 1 MUFU
 
-// Conservative ray / bounding-sphere test. Returns true and the (clamped) entry distance in ray
-// parameter units when the sphere, fattened by RT_CULL_SLACK * (|m|_1 + r), can contain a hit with
-// parameter in [0, tmax].
-RT_DEVICE bool cull_sphere(float4 s, f3 o, f3 d, float inv_dd, float tmax, float &t_entry) {
+// Conservative ray / bounding-sphere test. Returns true and the entry distance in ray parameter units when the
+// sphere, fattened by `slack`, can contain a hit with parameter in [0, tmax]. `slack` is per ray:
+// RT_CULL_SLACK * (|o|_1 + scene bound) >= RT_CULL_SLACK * (|c - o|_1 + r) for every node of the scene, i.e. proportional to
+// the largest distance at which the exact triangle arithmetic of this ray can still round differently.
+RT_DEVICE bool cull_sphere(float4 s, f3 o, f3 d, float inv_dd, float slack, float tmax, float &t_entry) {
     float mx = s.x - o.x, my = s.y - o.y, mz = s.z - o.z;
     float b = __fmaf_rn(mz, d.z, __fmaf_rn(my, d.y, mx * d.x));
     float tca = b * inv_dd;
     float px = __fmaf_rn(-tca, d.x, mx), py = __fmaf_rn(-tca, d.y, my), pz = __fmaf_rn(-tca, d.z, mz);
     float dist2 = __fmaf_rn(pz, pz, __fmaf_rn(py, py, px * px));
-    float r = __fmaf_rn(RT_CULL_SLACK, fabsf(mx) + fabsf(my) + fabsf(mz) + s.w, s.w);
+    float r = s.w + slack;
     float h2 = __fmaf_rn(r, r, -dist2);
-    if (!(h2 >= 0.0f)) return false;                    // also rejects NaN radii (empty child)
-    float half = approx_sqrt(h2 * inv_dd);
+    float half = approx_sqrt(fmaxf(h2, 0.0f) * inv_dd);
     float t0 = tca - half;
-    if (tca + half < 0.0f) return false;                // sphere entirely behind the origin
-    if (t0 > tmax) return false;                        // raytracer.cpp:177 (strict >)
     t_entry = t0;
-    return true;
+    // h2 >= 0 is false for NaN radii (empty child); strict > on tmax as raytracer.cpp:177
+    return (h2 >= 0.0f) & (tca + half >= 0.0f) & !(t0 > tmax);
 }
 
 struct RayCtx {
@@ -126,7 +125,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
 
     bool live = false, exhausted = false;
     RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
-    float inv_dd = 0.0f, dist_sq = -1.0f;
+    float inv_dd = 0.0f, dist_sq = -1.0f, slack = 0.0f;
     HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
     uint32_t best_rank = 0xFFFFFFFFu, out_idx = 0, light = 0;
     int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light)
@@ -166,6 +165,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                     f3 q = c.o + dir;
                     c.qp = c.o - q;
                     inv_dd = 1.0f / __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x));
+                    slack = RT_CULL_SLACK * (fabsf(c.o.x) + fabsf(c.o.y) + fabsf(c.o.z) + S.cull_bound);
                     best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1; best_rank = 0xFFFFFFFFu;   // raytracer.cpp:166
                     cur = S.root; sp = 0;
                     live = true;
@@ -183,16 +183,14 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                 int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 2));
                 float t0, t1;
                 // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
-                bool h0 = cull_sphere(s0, c.o, c.d, inv_dd, best.t, t0);
-                bool h1 = cull_sphere(s1, c.o, c.d, inv_dd, best.t, t1);
+                bool h0 = cull_sphere(s0, c.o, c.d, inv_dd, slack, best.t, t0);
+                bool h1 = cull_sphere(s1, c.o, c.d, inv_dd, slack, best.t, t1);
                 if (COUNT) n_sph += 2;
-                if (h0 && h1) {
-                    int near = ch.x, far = ch.y;
-                    if (t1 < t0) { near = ch.y; far = ch.x; }
-                    if (sp < RT_STACK_MAX) stack[sp++] = far;
-                    cur = near;
-                } else if (h0) cur = ch.x;
-                else if (h1) cur = ch.y;
+                bool second_first = h1 & (!h0 | (t1 < t0));
+                int near = second_first ? ch.y : ch.x;
+                int far = second_first ? ch.x : ch.y;
+                if (h0 & h1) stack[sp++] = far;                      // depth <= RT_STACK_MAX - 2 is guaranteed by the build
+                if (h0 | h1) cur = near;
                 else if (sp == 0) done = true;
                 else cur = stack[--sp];
             }
