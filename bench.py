@@ -217,9 +217,12 @@ def run_ours(args, rank, world, local_rank):
     total_spp = SPP * world if mode == "samples" else SPP
     p_job = params.copy(); p_job["min_samples"] = p_job["max_samples"] = total_spp
     TIMED = api.RT_FLAG_TIME_KERNELS
+    tile_ids = dist.tile_partition(WIDTH, HEIGHT, rank, world, 32) if mode == "tiles" else None
+    debug = os.environ.get("RT_BENCH_DEBUG") == "1"
 
     def step(flags_extra=0):
         """One Render() of the frame; device-resident output (+ the NCCL combine for N > 1)."""
+        t_s = time.time()
         flush.zero_()
         frame.zero_()
         if mode == "samples":
@@ -228,12 +231,15 @@ def run_ours(args, rank, world, local_rank):
             cnt = S.render_device(cam, p_job, WIDTH, HEIGHT, frame.data_ptr(), sample_begin=s0, sample_count=ns,
                                   flags=out_flags | flags_extra, stream=stream)
         else:
-            ids = dist.tile_partition(WIDTH, HEIGHT, rank, world, 32)
-            cnt = S.render_device(cam, p_job, WIDTH, HEIGHT, frame.data_ptr(), pixel_ids=ids, sample_count=total_spp,
+            cnt = S.render_device(cam, p_job, WIDTH, HEIGHT, frame.data_ptr(), pixel_ids=tile_ids, sample_count=total_spp,
                                   flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME | flags_extra, stream=stream)
         st = S.stats()
+        t_r = time.time()
         if world > 1:
             dist.combine_frame(frame, mode, total_spp, dst=0)
+        if debug:
+            torch.cuda.synchronize(dev)
+            print(f"[rank {rank}] step: render {1e3 * (t_r - t_s):.1f} ms wall (gpu {float(st['gpu_ms']):.1f}), combine+sync {1e3 * (time.time() - t_r):.1f} ms", file=sys.stderr)
         return int(cnt["ray_count"]), st
 
     def sync_all():

@@ -100,6 +100,10 @@ struct rt_scene {
     rt_stats stats{};
     Pool pool;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // grow-only scratch of render calls (no cudaMalloc / cudaFree -- an implicit device sync -- per frame)
+    float4 *accum = nullptr; size_t accum_cap = 0;
+    uint32_t *ids = nullptr; size_t ids_cap = 0;
+    float *out_stage = nullptr; size_t out_stage_cap = 0;
     std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
     size_t tev_used = 0;
     int sm_count = 148;
@@ -299,6 +303,9 @@ extern "C" void rt_scene_destroy(rt_scene *sc) {
     cudaSetDevice(sc->device);
     if (sc->stream) cudaStreamSynchronize(sc->stream);
     sc->pool.mem.release();
+    if (sc->accum) cudaFree(sc->accum);
+    if (sc->ids) cudaFree(sc->ids);
+    if (sc->out_stage) cudaFree(sc->out_stage);
     if (sc->pool.h_counts) cudaFreeHost(sc->pool.h_counts);
     for (int k = 0; k < 4; ++k) if (sc->pool.count_ev[k]) cudaEventDestroy(sc->pool.count_ev[k]);
     sc->mem.release();
@@ -519,6 +526,17 @@ static int ensure_spec_table(rt_scene *sc, uint32_t ss) {
     return RT_OK;
 }
 
+template <typename T> static int grow(rt_scene *sc, T **buf, size_t *cap, size_t need) {
+    if (*cap >= need && *buf) return RT_OK;
+    CK(cudaStreamSynchronize(sc->stream));
+    if (*buf) CK(cudaFree(*buf));
+    *buf = nullptr; *cap = 0;
+    size_t n = std::max<size_t>(need, 1);
+    CK(cudaMalloc((void **)buf, n * sizeof(T)));
+    *cap = n;
+    return RT_OK;
+}
+
 static DevParams to_dev_params(const rt_params *p) {
     DevParams d;
     d.ray_bias = p->ray_bias; d.reflection_samples = p->reflection_samples; d.spec_samples = p->spec_samples;
@@ -696,11 +714,15 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
     DevArena tmp;
     auto done = [&](int r) { tmp.release(); return r; };
 #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
-    float4 *accum; uint32_t *d_ids = nullptr;
-    CKR(tmp.alloc(&accum, pixel_count));
+    uint32_t *d_ids = nullptr;
+    rc = grow(sc, &sc->accum, &sc->accum_cap, pixel_count);
+    if (rc) return done(rc);
+    float4 *accum = sc->accum;
     CKR(cudaMemsetAsync(accum, 0, (size_t)pixel_count * sizeof(float4), st));
     if (pixel_ids) {
-        CKR(tmp.alloc(&d_ids, pixel_count));
+        rc = grow(sc, &sc->ids, &sc->ids_cap, pixel_count);
+        if (rc) return done(rc);
+        d_ids = sc->ids;
         CKR(cudaMemcpyAsync(d_ids, pixel_ids, (size_t)pixel_count * 4, cudaMemcpyHostToDevice, st));
         sc->stats.h2d_bytes += (uint64_t)pixel_count * 4;
     }
@@ -764,9 +786,10 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params 
     if (!scene || !out_rgba_host) return fail(RT_ERR_ARG, "null argument");
     if (flags & RT_OUT_FULLFRAME) return fail(RT_ERR_ARG, "RT_OUT_FULLFRAME is a device-output mode");
     CK(cudaSetDevice(scene->device));
-    float *d_out = nullptr;
-    CK(cudaMalloc((void **)&d_out, std::max<size_t>(1, (size_t)pixel_count) * 16));
-    int rc = render_impl(scene, cam, params, width, height, pixel_ids, pixel_begin, pixel_count, sample_begin, sample_count, flags,
+    int rc = grow(scene, &scene->out_stage, &scene->out_stage_cap, (size_t)pixel_count * 4);
+    if (rc) return rc;
+    float *d_out = scene->out_stage;
+    rc = render_impl(scene, cam, params, width, height, pixel_ids, pixel_begin, pixel_count, sample_begin, sample_count, flags,
                          d_out, nullptr, out_counters);
     if (rc == RT_OK && pixel_count) {
         cudaError_t e = cudaMemcpyAsync(out_rgba_host, d_out, (size_t)pixel_count * 16, cudaMemcpyDeviceToHost, scene->stream);
@@ -774,7 +797,6 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params 
         if (e != cudaSuccess) rc = fail(RT_ERR_CUDA, "framebuffer download failed: %s", cudaGetErrorString(e));
         scene->stats.d2h_bytes += (uint64_t)pixel_count * 16;
     }
-    cudaFree(d_out);
     return rc;
 }
 
