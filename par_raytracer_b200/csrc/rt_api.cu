@@ -184,13 +184,14 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
 
     uint32_t n_pad = BITONIC_TILE;
     while (n_pad < n) n_pad <<= 1;
-    float4 *tri_sphere, *tri_lo, *tri_hi; uint32_t *bounds; uint64_t *keys; uint32_t *vals;
-    CKB(tmp.alloc(&tri_sphere, n)); CKB(tmp.alloc(&tri_lo, n)); CKB(tmp.alloc(&tri_hi, n)); CKB(tmp.alloc(&bounds, 8)); CKB(tmp.alloc(&keys, n_pad)); CKB(tmp.alloc(&vals, n_pad));
+    float4 *tri_sphere, *tri_lo, *tri_hi, *tri_nrm0, *tri_slab; uint32_t *bounds; uint64_t *keys; uint32_t *vals;
+    CKB(tmp.alloc(&tri_sphere, n)); CKB(tmp.alloc(&tri_lo, n)); CKB(tmp.alloc(&tri_hi, n)); CKB(tmp.alloc(&tri_nrm0, n)); CKB(tmp.alloc(&tri_slab, n));
+    CKB(tmp.alloc(&bounds, 8)); CKB(tmp.alloc(&keys, n_pad)); CKB(tmp.alloc(&vals, n_pad));
     {
         uint32_t hb[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
         CKB(cudaMemcpyAsync(bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
     }
-    k_tri_spheres<<<cdiv(n, 256), 256, 0, st>>>(bin, tri_sphere, tri_lo, tri_hi, bounds); CKLB("k_tri_spheres");
+    k_tri_spheres<<<cdiv(n, 256), 256, 0, st>>>(bin, tri_sphere, tri_lo, tri_hi, tri_nrm0, tri_slab, bounds); CKLB("k_tri_spheres");
     k_morton<<<cdiv(n_pad, 256), 256, 0, st>>>(n, n_pad, tri_sphere, bounds, keys, vals); CKLB("k_morton");
     // bitonic sort
     k_bitonic_shared<<<n_pad / BITONIC_TILE, 1024, 0, st>>>(keys, vals, 2, BITONIC_TILE, 0); CKLB("k_bitonic_shared");
@@ -206,7 +207,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     TempTree t;
     CKB(tmp.alloc(&t.c0, n_total)); CKB(tmp.alloc(&t.c1, n_total)); CKB(tmp.alloc(&t.parent, n_total));
     CKB(tmp.alloc(&t.size, n_total)); CKB(tmp.alloc(&t.kept, n_total)); CKB(tmp.alloc(&t.sphere, n_total));
-    CKB(tmp.alloc(&t.lo, n_total)); CKB(tmp.alloc(&t.hi, n_total));
+    CKB(tmp.alloc(&t.lo, n_total)); CKB(tmp.alloc(&t.hi, n_total)); CKB(tmp.alloc(&t.nsum, n_total)); CKB(tmp.alloc(&t.slab, n_total));
     int32_t *cn[2]; uint32_t *nn, *slot_tri; uint64_t *flags, *scan, *bsums, *total;
     CKB(tmp.alloc(&cn[0], n)); CKB(tmp.alloc(&cn[1], n)); CKB(tmp.alloc(&slot_tri, n));
     CKB(tmp.alloc(&nn, n)); CKB(tmp.alloc(&flags, n)); CKB(tmp.alloc(&scan, n));
@@ -218,7 +219,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     int32_t root_temp = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
         const int pair_mode = attempt;       // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n)
-        k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, tri_lo, tri_hi, cn[0], t); CKLB("k_ploc_init");
+        k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, tri_lo, tri_hi, tri_nrm0, tri_slab, cn[0], t); CKLB("k_ploc_init");
         uint32_t m = n, created = 0;
         int cur = 0;
         iterations = 0;

@@ -80,7 +80,8 @@ struct BuildInput {
 
 RT_DEVICE f3 ld3(const float *p, uint32_t i) { return mk3(p[3 * (size_t)i], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]); }
 
-__global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, float4 *tri_lo, float4 *tri_hi, uint32_t *bounds /*6 flipped floats*/) {
+__global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, float4 *tri_lo, float4 *tri_hi, float4 *tri_nrm, float4 *tri_slab,
+                              uint32_t *bounds /*6 flipped floats*/) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     f3 lo = mk3(FLT_MAX, FLT_MAX, FLT_MAX), hi = mk3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
     if (j < in.n_tris) {
@@ -109,6 +110,17 @@ __global__ void k_tri_spheres(BuildInput in, float4 *tri_sphere, float4 *tri_lo,
         if (!(r2 < FLT_MAX)) { ctr = (a + b + c) * (1.0f / 3.0f); da = a - ctr; db = b - ctr; dc = c - ctr;
                                 r2 = fmaxf(dot3(da, da), fmaxf(dot3(db, db), dot3(dc, dc))); }
         tri_sphere[j] = make_float4(ctr.x, ctr.y, ctr.z, sqrtf(r2) * 1.000002f + 1e-30f);
+        {
+            f3 nn = cross3(b - a, c - a);                                  // area-weighted normal (sums give a subtree's mean normal)
+            tri_nrm[j] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+            float l = sqrtf(dot3(nn, nn));
+            if (l > 0.0f && l < FLT_MAX) {
+                f3 u = nn * (1.0f / l);
+                float da = dot3(u, a), db = dot3(u, b), dc = dot3(u, c);
+                tri_slab[j] = make_float4(u.x, u.y, u.z, fminf(da, fminf(db, dc)));
+                tri_nrm[j].w = fmaxf(da, fmaxf(db, dc));               // dmax rides in the normal's w
+            } else { tri_slab[j] = make_float4(0, 0, 0, -FLT_MAX); tri_nrm[j].w = FLT_MAX; }
+        }
         tri_lo[j] = make_float4(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)), 0.0f);
         tri_hi[j] = make_float4(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)), 0.0f);
         lo = ctr; hi = ctr;
@@ -253,16 +265,19 @@ struct TempTree {           // 2n - 1 nodes: [0, n) = sorted triangles, [n, 2n-1
     uint32_t *kept;          // internal nodes with size > RT_LEAF_MAX in subtree (incl. self)
     float4 *sphere;
     float4 *lo, *hi;         // exact axis-aligned bounds of the subtree's vertices
+    float4 *nsum;            // xyz: sum of area-weighted triangle normals of the subtree; w: slab dmax
+    float4 *slab;            // unit normal xyz + dmin (0, 0, 0, -FLT_MAX: no slab)
 };
 
 __global__ void k_ploc_init(uint32_t n, const uint32_t *sorted_tri, const float4 *tri_sphere, const float4 *tri_lo, const float4 *tri_hi,
-                            int32_t *cl_node, TempTree t) {
+                            const float4 *tri_nrm, const float4 *tri_slab, int32_t *cl_node, TempTree t) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t j = sorted_tri[i];
     cl_node[i] = (int32_t)i;
     t.c0[i] = -1; t.c1[i] = -1; t.parent[i] = -1; t.size[i] = 1; t.kept[i] = 0; t.sphere[i] = tri_sphere[j];
     t.lo[i] = tri_lo[j]; t.hi[i] = tri_hi[j];
+    t.nsum[i] = tri_nrm[j]; t.slab[i] = tri_slab[j];
 }
 
 // Search cost = squared diagonal of the merged bounds, i.e. (2 x radius)^2 of the sphere around the merged box:
@@ -324,6 +339,9 @@ __global__ void k_ploc_merge(uint32_t m, uint32_t n, uint32_t nodes_created, con
         float4 la = t.lo[a], lb = t.lo[b], ha = t.hi[a], hb = t.hi[b];
         t.lo[id] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
         t.hi[id] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+        float4 na = t.nsum[a], nb = t.nsum[b];
+        t.nsum[id] = make_float4(na.x + nb.x, na.y + nb.y, na.z + nb.z, FLT_MAX);
+        t.slab[id] = make_float4(0, 0, 0, -FLT_MAX);
         out_node[pos] = id;
     } else {
         out_node[pos] = cl_node[i];
@@ -368,18 +386,31 @@ __global__ void __launch_bounds__(256) k_refit(uint32_t n, uint32_t n_total, Tem
     float4 lo = t.lo[v], hi = t.hi[v];
     f3 ctr = mk3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
     uint32_t off = tri_offset[v], size = t.size[v];
-    float d2 = 0.0f;
+    float4 ns = t.nsum[v];
+    float nl = sqrtf(ns.x * ns.x + ns.y * ns.y + ns.z * ns.z);
+    bool has_n = nl > 0.0f && nl < FLT_MAX;
+    f3 u = has_n ? mk3(ns.x / nl, ns.y / nl, ns.z / nl) : mk3(0, 0, 0);
+    float d2 = 0.0f, pmin = FLT_MAX, pmax = -FLT_MAX;
     for (uint32_t k = lane; k < size; k += 32u) {
         uint32_t j = slot_tri[off + k];
         for (int c = 0; c < 3; ++c) {
-            f3 p = ld3(in.positions, in.idx_positions[3 * (size_t)j + c]) - ctr;
+            f3 q = ld3(in.positions, in.idx_positions[3 * (size_t)j + c]);
+            f3 p = q - ctr;
             d2 = fmaxf(d2, dot3(p, p));
+            float pr = dot3(u, q);
+            pmin = fminf(pmin, pr); pmax = fmaxf(pmax, pr);
         }
     }
-    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+        pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+        pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+    }
     if (lane == 0) {
         float r = sqrtf(d2) * 1.000002f + 1e-30f;
         if (r < t.sphere[v].w) t.sphere[v] = make_float4(ctr.x, ctr.y, ctr.z, r);
+        // a slab thicker than ~the sphere prunes nothing: leave it disabled
+        if (has_n && (pmax - pmin) < 1.5f * t.sphere[v].w) { t.slab[v] = make_float4(u.x, u.y, u.z, pmin); t.nsum[v].w = pmax; }
     }
 }
 
@@ -391,9 +422,10 @@ __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, con
     HNode o;
     int32_t a = t.c0[v], b = t.c1[v];
     o.s0 = t.sphere[a]; o.s1 = t.sphere[b];
+    o.p0 = t.slab[a]; o.p1 = t.slab[b];
+    o.dmax0 = t.nsum[a].w; o.dmax1 = t.nsum[b].w;
     o.c0 = t.size[a] > RT_LEAF_MAX ? (int32_t)kept_index[a] : leaf_ref(tri_offset[a], t.size[a]);
     o.c1 = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
-    o.pad0 = t.size[v]; o.pad1 = 0;
     nodes[kept_index[v]] = o;
 }
 

@@ -45,16 +45,20 @@ RT_DEVICE float4 mk4u(f3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __ui
 // device-resident scene
 // ---------------------------------------------------------------------------------------------
 
-// One node of the GPU-built bounding-sphere hierarchy: the spheres of BOTH children live in the
-// parent (one 48-byte fetch decides both descents). child >= 0: node index; child < 0: cluster
-// (leaf) encoded as -(1 + first_triangle * 8 + triangle_count), triangle_count <= 7.
+// One node of the GPU-built bounding-sphere hierarchy: the bounds of BOTH children live in the parent (one 80-byte
+// fetch decides both descents). Each child is bounded by a sphere and, inside it, by a slab: the sphere says where the
+// subtree is, the slab (unit normal n = the subtree's mean triangle normal, dmin <= n.v <= dmax for every vertex v) says how
+// thin it is -- surface patches are thin shells, and a sphere alone admits every ray that grazes them.
+// child >= 0: node index; child < 0: cluster (leaf) encoded as -(1 + first_triangle * 8 + triangle_count), count <= 7.
 struct __align__(16) HNode {
     float4 s0;          // child 0: center.xyz, radius
     float4 s1;          // child 1
+    float4 p0;          // child 0 slab: n.xyz, dmin        (n = 0, dmin = -inf: no slab)
+    float4 p1;          // child 1 slab
+    float dmax0, dmax1;
     int32_t c0, c1;
-    uint32_t pad0, pad1;
 };
-static_assert(sizeof(HNode) == 48, "HNode");
+static_assert(sizeof(HNode) == 80, "HNode");
 
 RT_DEVICE int leaf_ref(uint32_t first, uint32_t count) { return -(int)(1u + first * 8u + count); }
 RT_DEVICE uint32_t leaf_first(int ref) { return ((uint32_t)(-ref) - 1u) >> 3; }

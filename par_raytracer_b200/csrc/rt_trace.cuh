@@ -34,11 +34,15 @@ struct TraceCounters { unsigned long long sphere_checks, cluster_checks; };
 
 RT_DEVICE float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // culling only: 1 MUFU
 
-// Conservative ray / bounding-sphere test. Returns true and the entry distance in ray parameter units when the
-// sphere, fattened by `slack`, can contain a hit with parameter in [0, tmax]. `slack` is per ray:
-// RT_CULL_SLACK * (|o|_1 + scene bound) >= RT_CULL_SLACK * (|c - o|_1 + r) for every node of the scene, i.e. proportional to
-// the largest distance at which the exact triangle arithmetic of this ray can still round differently.
-RT_DEVICE bool cull_sphere(float4 s, f3 o, f3 d, float inv_dd, float slack, float tmax, float &t_entry) {
+// Conservative test of a ray against one child bound = (sphere fattened by `slack`) INTERSECT (slab fattened by `slack`).
+//   sphere: distance from the centre to the ray line through the perpendicular foot (robust; no b*b - c cancellation),
+//           giving the parameter interval [tca - half, tca + half], clipped to [0, tmax];
+//   slab:   over that clipped interval [T0, T1], n.(o + t d) - n.o sweeps [min(T0 nd, T1 nd), max(T0 nd, T1 nd)], which must
+//           meet [dmin - slack - n.o, dmax + slack - n.o]. No division, no special case for rays parallel to the slab.
+// `slack` is per ray: RT_CULL_SLACK * (|o|_1 + scene bound) >= RT_CULL_SLACK * (|c - o|_1 + r) for every node, i.e. proportional
+// to the largest distance at which this ray's exact triangle arithmetic can still round differently. FMA and approximate
+// sqrt are allowed here: the result only prunes. Returns the sphere entry distance for near/far ordering.
+RT_DEVICE bool cull_child(float4 s, float4 p, float dmax, f3 o, f3 d, float inv_dd, float slack, float tmax, float &t_entry) {
     float mx = s.x - o.x, my = s.y - o.y, mz = s.z - o.z;
     float b = __fmaf_rn(mz, d.z, __fmaf_rn(my, d.y, mx * d.x));
     float tca = b * inv_dd;
@@ -47,10 +51,15 @@ RT_DEVICE bool cull_sphere(float4 s, f3 o, f3 d, float inv_dd, float slack, floa
     float r = s.w + slack;
     float h2 = __fmaf_rn(r, r, -dist2);
     float half = approx_sqrt(fmaxf(h2, 0.0f) * inv_dd);
-    float t0 = tca - half;
+    float t0 = tca - half, t1 = tca + half;
     t_entry = t0;
-    // h2 >= 0 is false for NaN radii (empty child); strict > on tmax as raytracer.cpp:177
-    return (h2 >= 0.0f) & (tca + half >= 0.0f) & !(t0 > tmax);
+    float T0 = fmaxf(t0, 0.0f), T1 = fminf(t1, tmax);
+    float no = __fmaf_rn(p.z, o.z, __fmaf_rn(p.y, o.y, p.x * o.x));
+    float nd = __fmaf_rn(p.z, d.z, __fmaf_rn(p.y, d.y, p.x * d.x));
+    float e0 = T0 * nd, e1 = T1 * nd;
+    float lo = (p.w - slack) - no, hi = (dmax + slack) - no;
+    // h2 >= 0 is false for NaN radii (empty child); T0 <= T1 <=> the sphere interval meets [0, tmax] (strict > on tmax as raytracer.cpp:177)
+    return (h2 >= 0.0f) & (T0 <= T1) & !((fmaxf(e0, e1) < lo) | (fminf(e0, e1) > hi));
 }
 
 struct RayCtx {
@@ -179,12 +188,13 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
             // ---- descend to the next cluster ----
             while (!done && cur >= 0) {
                 const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
-                float4 s0 = __ldg(np), s1 = __ldg(np + 1);
-                int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 2));
+                float4 s0 = __ldg(np), s1 = __ldg(np + 1), p0 = __ldg(np + 2), p1 = __ldg(np + 3);
+                float4 m4 = __ldg(np + 4);
+                int2 ch = make_int2(__float_as_int(m4.z), __float_as_int(m4.w));
                 float t0, t1;
                 // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
-                bool h0 = cull_sphere(s0, c.o, c.d, inv_dd, slack, best.t, t0);
-                bool h1 = cull_sphere(s1, c.o, c.d, inv_dd, slack, best.t, t1);
+                bool h0 = cull_child(s0, p0, m4.x, c.o, c.d, inv_dd, slack, best.t, t0);
+                bool h1 = cull_child(s1, p1, m4.y, c.o, c.d, inv_dd, slack, best.t, t1);
                 if (COUNT) n_sph += 2;
                 bool second_first = h1 & (!h0 | (t1 < t0));
                 int near = second_first ? ch.y : ch.x;
