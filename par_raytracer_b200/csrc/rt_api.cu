@@ -16,6 +16,7 @@
 #include "rt_build.cuh"
 #include "rt_common.cuh"
 #include "rt_rng.cuh"
+#include "rt_raygen.cuh"
 #include "rt_shade.cuh"
 #include "rt_trace.cuh"
 
@@ -598,12 +599,14 @@ static WaveQueues wave_queues(rt_scene *sc, int cur, uint32_t n_closest_max) {
     return w;
 }
 
-static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, uint64_t work_bound, bool count, TraceCounters *tc) {
+static PrimaryGen no_gen() { PrimaryGen g; memset(&g, 0, sizeof(g)); return g; }
+
+static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, const PrimaryGen &gen, uint64_t work_bound, bool count, TraceCounters *tc) {
     cudaStream_t st = sc->stream;
     CK(cudaMemsetAsync(w.next, 0, 4, st));
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sc->trace_grid, std::max<uint64_t>(1, (work_bound + RT_TRACE_BLOCK - 1) / RT_TRACE_BLOCK));
-    if (count) k_trace_wave<true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, tc);
-    else k_trace_wave<false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, tc);
+    if (count) k_trace_wave<true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
+    else k_trace_wave<false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
     CKL("k_trace_wave");
     return RT_OK;
 }
@@ -615,7 +618,7 @@ static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, uint
 // enqueued -- with launch bounds taken from the newest counts the host already has -- BEFORE the host waits for
 // wave w's 16-byte count read-back. The read-backs only decide when to stop and feed the statistics.
 #define RT_COUNT_RING 4
-static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint32_t flags, uint64_t *launches) {
+static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint32_t flags, uint64_t *launches, const PrimaryGen *first_gen = nullptr) {
     const bool timed = (flags & RT_FLAG_TIME_KERNELS) != 0;
     Pool &p = sc->pool;
     cudaStream_t st = sc->stream;
@@ -629,11 +632,12 @@ static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint3
     auto issue = [&](uint32_t w) -> int {
         const int cur = (int)(w & 1u);
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
-        { int rc_ = launch_trace_wave(sc, prm.ray_bias, wave_queues(sc, cur, bound), (uint64_t)bound * (1 + L), count, p.tcount); if (rc_) return rc_; }
+        const PrimaryGen gen = (w == 0 && first_gen) ? *first_gen : no_gen();     // wave 0 of a render: rays are generated in place
+        { int rc_ = launch_trace_wave(sc, prm.ray_bias, wave_queues(sc, cur, bound), gen, (uint64_t)bound * (1 + L), count, p.tcount); if (rc_) return rc_; }
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
         if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
-        k_logic<<<cdiv(std::max(1u, bound), 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow);
+        k_logic<<<cdiv(std::max(1u, bound), 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow, gen);
         CKL("k_logic");
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
@@ -736,11 +740,11 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
         for (uint32_t s0 = 0; s0 < sample_count; s0 += spp_chunk) {
             const uint32_t ns = std::min(spp_chunk, sample_count - s0);
             const uint32_t n_slots = npix * ns;
-            k_raygen<<<cdiv(n_slots, 256), 256, 0, st>>>(dcam, prm, p.paths, p.q[0], n_slots, ns, width, d_ids, pixel_begin, p0,
-                                                        sample_begin + s0, 0.5f, p.counts);
-            { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_raygen failed: %s", cudaGetErrorString(e_))); }
-            launches++;
-            rc = run_waves(sc, prm, n_slots, flags, &launches);
+            PrimaryGen gen;
+            memset(&gen, 0, sizeof(gen));
+            gen.cam = dcam; gen.base_seed = prm.base_seed; gen.pixel_ids = d_ids; gen.n_slots = n_slots; gen.spp = ns; gen.width = width;
+            gen.pixel_begin = pixel_begin; gen.pixel_local0 = p0; gen.sample_begin = sample_begin + s0; gen.jitter_scale = 0.5f; gen.enabled = 1;
+            rc = run_waves(sc, prm, n_slots, flags, &launches, &gen);
             if (rc) return done(rc);
             k_resolve<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, p0);
             { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_resolve failed: %s", cudaGetErrorString(e_))); }
@@ -833,13 +837,13 @@ extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray
         if (mode == RT_TRACE_ANY) {
             k_rays_to_shadow_queue<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q.o, q.d, rad, acc, cnt);
             w.closest_max = 0; w.n_lights = 1;
-            rc = launch_trace_wave(sc, params->ray_bias, w, m, true, tc);
+            rc = launch_trace_wave(sc, params->ray_bias, w, no_gen(), m, true, tc);
             k_occlusion_to_api<<<cdiv(m, 256), 256, 0, st>>>(acc, m, api);
         } else {
             k_upload_rays<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q);
             w.closest_max = m; w.n_lights = 0;
             if (mode == RT_TRACE_BRUTE) k_trace_brute<<<cdiv(m, 128), 128, 0, st>>>(sc->d, params->ray_bias, q, m, hits);
-            else rc = launch_trace_wave(sc, params->ray_bias, w, m, true, tc);
+            else rc = launch_trace_wave(sc, params->ray_bias, w, no_gen(), m, true, tc);
             k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, params->ray_bias, q, hits, m, api);
         }
         if (rc) return done(rc);
@@ -896,11 +900,15 @@ extern "C" int rt_trace_primary(rt_scene *sc, const rt_camera *cam, const rt_par
         for (uint32_t s0 = 0; s0 < sample_count; s0 += spp_chunk) {
             const uint32_t ns = std::min(spp_chunk, sample_count - s0);
             const uint32_t m = npix * ns;
-            k_raygen<<<cdiv(m, 256), 256, 0, st>>>(dcam, prm, p.paths, p.q[0], m, ns, width, d_ids, pixel_begin, p0, sample_begin + s0, 0.5f, p.counts);
+            PrimaryGen gen;
+            memset(&gen, 0, sizeof(gen));
+            gen.cam = dcam; gen.base_seed = prm.base_seed; gen.pixel_ids = d_ids; gen.n_slots = m; gen.spp = ns; gen.width = width;
+            gen.pixel_begin = pixel_begin; gen.pixel_local0 = p0; gen.sample_begin = sample_begin + s0; gen.jitter_scale = 0.5f; gen.enabled = 1;
+            k_raygen<<<cdiv(m, 256), 256, 0, st>>>(gen, prm, p.paths, p.q[0], p.counts);
             if (out_hits) {
                 WaveQueues w = wave_queues(sc, 0, m);
                 w.n_closest = nullptr; w.n_lights = 0;
-                rc = launch_trace_wave(sc, prm.ray_bias, w, m, false, p.tcount);
+                rc = launch_trace_wave(sc, prm.ray_bias, w, no_gen(), m, false, p.tcount);
                 if (rc) return done(rc);
                 k_hits_to_api<<<cdiv(m, 256), 256, 0, st>>>(sc->d, prm.ray_bias, p.q[0], p.hits, m, api);
                 sc->stats.kernel_launches += 2; sc->stats.closest_rays += m;

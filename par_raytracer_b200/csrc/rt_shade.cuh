@@ -20,6 +20,7 @@
 #pragma once
 #include "rt_common.cuh"
 #include "rt_rng.cuh"
+#include "rt_raygen.cuh"
 #include "rt_trace.cuh"
 
 #define RT_FRAME_F4 6            // float4 words per recursion frame
@@ -52,45 +53,21 @@ RT_DEVICE uint32_t warp_push(uint32_t *counter, bool pred) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
-// ---- main.cpp:164-177 MakeCameraRay ------------------------------------------------------------------
-struct DevCamera { float tan_a2, aspect, inv_width, inv_height; float pos[3], fwd[3], right[3], up[3]; };
-
-RT_DEVICE void camera_ray(const DevCamera &cam, float ox, float oy, f3 &org, f3 &dir) {
-    float nx = 2.0f * (ox + 0.5f) * cam.inv_width - 1.0f;
-    float ny = 1.0f - 2.0f * (oy + 0.5f) * cam.inv_height;
-    f3 fwd = mk3(cam.fwd[0], cam.fwd[1], cam.fwd[2]);
-    f3 right = mk3(cam.right[0], cam.right[1], cam.right[2]);
-    f3 up = mk3(cam.up[0], cam.up[1], cam.up[2]);
-    f3 a = ((right * cam.tan_a2) * cam.aspect) * nx;
-    f3 b = (up * cam.tan_a2) * ny;
-    dir = normalize3((fwd + a) + b);
-    org = mk3(cam.pos[0], cam.pos[1], cam.pos[2]);
-}
-
 // ---- K1: ray generation = RenderPixel's per-sample prologue (main.cpp:237-241 / 246-250) ---------------
 // slot s of the batch <-> (pixel_local = s / spp, sample = sample_begin + s % spp)
-__global__ void k_raygen(DevCamera cam, DevParams prm, PathPool P, RayQueue q, uint32_t n_slots, uint32_t spp, uint32_t width,
-                         const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_local0, uint32_t sample_begin,
-                         float jitter_scale, uint32_t *n_rays_out) {
+__global__ void k_raygen(PrimaryGen g, DevParams prm, PathPool P, RayQueue q, uint32_t *n_rays_out) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_slots) return;
-    uint32_t pl = pixel_local0 + s / spp;
-    uint32_t samp = sample_begin + s % spp;
-    uint32_t pixel = pixel_ids ? pixel_ids[pl] : pixel_begin + pl;
-    uint32_t x = pixel % width, y = pixel / width;           // main.cpp:274-275
+    if (s >= g.n_slots) return;
     PathRng r;
-    rng_seed(r, sample_seed(prm.base_seed, pixel, samp));
-    float jy = rng_float11(r);                               // y takes the first draw
-    float jx = rng_float11(r);
     f3 org, dir;
-    camera_ray(cam, (float)x + jx * jitter_scale, (float)y + jy * jitter_scale, org, dir);
+    primary_ray(g, s, r, org, dir);
     q.o[s] = mk4(org, 0.0f);
     q.d[s] = mk4u(dir, s);
     P.rng_seed[s] = r.seed;
     P.rng_cx[s] = rng_pack(r);
     P.acc[s] = make_float4(0, 0, 0, 0);
     P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
-    if (s == 0) *n_rays_out = n_slots;
+    if (s == 0) *n_rays_out = g.n_slots;
 }
 
 // paths started from caller-supplied rays and seeds (rt_trace_color <-> TraceRayColor)
@@ -183,8 +160,8 @@ struct ShadowQueue { float4 *o; float4 *rad; uint32_t *count; uint32_t capacity;
 #define RT_LOGIC_MIN_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
-                                              uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh) {
-    uint32_t n_in = min(*n_in_ptr, n_in_max);
+                                              uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh, PrimaryGen G) {
+    uint32_t n_in = G.enabled ? G.n_slots : min(*n_in_ptr, n_in_max);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n_in;
     const uint32_t cap = P.capacity;
@@ -203,19 +180,27 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
     float spec_int = 0.0f, w_diffuse = 0.0f;
 
     if (active) {
-        // every independent load of the path's state is issued before the first use
-        float4 o4 = qin.o[i], d4 = qin.d[i];
         HitRec h = hits[i];
-        slot = __float_as_uint(d4.w);
-        float4 t4 = P.node_T[slot];
-        uint4 cx = P.rng_cx[slot];
-        float4 a4 = P.acc[slot];
-        uint32_t st = __float_as_uint(t4.w);
-        T = mk3(t4); iters = (int)(st & 0xFFu); sp = (st >> 8) & 0xFFu;
-        rng_unpack(cx, st >> 16, rng);
-        if (rng.n >= 15u) rng.seed = P.rng_seed[slot];
-        acc = mk3(a4);
-        f3 org = mk3(o4); V = mk3(d4);
+        f3 org;
+        if (G.enabled) {
+            // wave 0: the primary ray and the fresh path state are recomputed, not streamed (rt_raygen.cuh)
+            slot = i;
+            primary_ray(G, i, rng, org, V);
+            T = mk3(1.0f, 1.0f, 1.0f); iters = bd; sp = 0;
+        } else {
+            // every independent load of the path's state is issued before the first use
+            float4 o4 = qin.o[i], d4 = qin.d[i];
+            slot = __float_as_uint(d4.w);
+            float4 t4 = P.node_T[slot];
+            uint4 cx = P.rng_cx[slot];
+            float4 a4 = P.acc[slot];
+            uint32_t st = __float_as_uint(t4.w);
+            T = mk3(t4); iters = (int)(st & 0xFFu); sp = (st >> 8) & 0xFFu;
+            rng_unpack(cx, st >> 16, rng);
+            if (rng.n >= 15u) rng.seed = P.rng_seed[slot];
+            acc = mk3(a4);
+            org = mk3(o4); V = mk3(d4);
+        }
 
         if (h.tri < 0) {
             acc = acc + T * mk3(prm.bg[0], prm.bg[1], prm.bg[2]);          // raytracer.cpp:573-575
@@ -380,9 +365,11 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             emit = true; e_org = c_org; e_dir = c_dir; e_T = c_T; e_iters = f_iters - 1;
         }
         P.acc[slot] = mk4(acc, 0.0f);
-        P.rng_cx[slot] = rng_pack(rng);
-        f3 Tn = emit ? e_T : T;
-        P.node_T[slot] = mk4u(Tn, pack_state(emit ? e_iters : iters, sp, rng.n));
+        if (emit) {                                    // a finished path only leaves its radiance behind
+            P.rng_cx[slot] = rng_pack(rng);
+            P.node_T[slot] = mk4u(e_T, pack_state(e_iters, sp, rng.n));
+            if (G.enabled) P.rng_seed[slot] = rng.seed;
+        }
     }
 
     // K6: compaction -- the next wave's queue holds only rays that exist

@@ -15,6 +15,7 @@
 //    the ray origin, so float rounding can never prune a triangle the exact test would accept.
 #pragma once
 #include "rt_common.cuh"
+#include "rt_raygen.cuh"
 
 #define RT_STACK_MAX 64
 #define RT_CULL_SLACK 4e-6f
@@ -124,10 +125,10 @@ struct WaveQueues {
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float bias, WaveQueues W, TraceCounters *counters) {
+__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float bias, WaveQueues W, PrimaryGen G, TraceCounters *counters) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t nC = W.n_closest ? min(*W.n_closest, W.closest_max) : W.closest_max;
+    const uint32_t nC = G.enabled ? G.n_slots : (W.n_closest ? min(*W.n_closest, W.closest_max) : W.closest_max);
     uint32_t total = nC;
     for (uint32_t l = 0; l < W.n_lights; ++l) total += min(W.n_shadow[l], W.shadow_stride);
     unsigned long long n_sph = 0, n_clu = 0;
@@ -153,7 +154,11 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                 uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < total) {
                     float4 o4, d4;
-                    if (idx < nC) { o4 = W.closest.o[idx]; d4 = W.closest.d[idx]; kind = 0; out_idx = idx; }
+                    if (idx < nC) {
+                        kind = 0; out_idx = idx;
+                        if (G.enabled) { PathRng pr; f3 po, pd; primary_ray(G, idx, pr, po, pd); o4 = mk4(po, 0.0f); d4 = mk4(pd, 0.0f); }
+                        else { o4 = W.closest.o[idx]; d4 = W.closest.d[idx]; }
+                    }
                     else {
                         uint32_t j = idx - nC; light = 0;
                         while (true) { uint32_t ns = min(W.n_shadow[light], W.shadow_stride); if (j < ns) break; j -= ns; light++; }
