@@ -184,7 +184,8 @@ typedef struct rt_scene rt_scene;           /* opaque device-resident scene + GP
 #define RT_OUT_FULLFRAME   2u               /* device output is a W*H frame; pixel p is written at p, others untouched */
 #define RT_FLAG_COUNTERS   4u               /* also count sphere / cluster tests (slower) */
 #define RT_FLAG_TIME_KERNELS 8u             /* CUDA-event-time the trace kernels (adds events, no syncs) */
-#define RT_FLAG_ADAPTIVE   16u              /* run RenderPixel's adaptive second loop when min_samples < max_samples */
+#define RT_FLAG_ADAPTIVE   16u              /* RenderPixel's adaptive second loop (main.cpp:245-258): min_samples fixed samples, then up to
+                                               max_samples with the variance test; sample_count is ignored */
 
 /* ---- lifecycle ------------------------------------------------------------------ */
 
@@ -256,6 +257,10 @@ int rt_trace_color(rt_scene *scene, const rt_params *params, const rt_ray *rays,
 
 /* ---- introspection --------------------------------------------------------------- */
 int rt_get_stats(const rt_scene *scene, rt_stats *out);
+
+/* Per-pixel sample counts -- RenderPixel's final `samp` (main.cpp:262) -- of the last render on this scene that ran
+ * with RT_FLAG_ADAPTIVE and min_samples < max_samples; n <= that render's pixel_count, order of its pixel list. */
+int rt_get_sample_counts(rt_scene *scene, uint32_t *out_host, uint32_t n);
 
 /* GPU-built hierarchy facts: out[0]=triangles, [1]=clusters(leaves), [2]=nodes, [3]=max depth,
  * [4]=bytes of node array, [5]=bytes of triangle records, [6]=build microseconds, [7]=reserved */

@@ -23,11 +23,12 @@ from .types import CAMERA, COUNTERS, HIT, PARAMS, RAY, STATS, SceneData
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 
-RT_OUT_MEAN, RT_OUT_SUM, RT_OUT_FULLFRAME, RT_FLAG_COUNTERS, RT_FLAG_TIME_KERNELS = 0, 1, 2, 4, 8
+RT_OUT_MEAN, RT_OUT_SUM, RT_OUT_FULLFRAME, RT_FLAG_COUNTERS, RT_FLAG_TIME_KERNELS, RT_FLAG_ADAPTIVE = 0, 1, 2, 4, 8, 16
 RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
-           "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat"]
+           "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat",
+           "rt_get_sample_counts"]
 
 
 class RtError(RuntimeError):
@@ -103,6 +104,12 @@ class Scene:
         _check(self.lib.rt_get_hierarchy_info(self.h, _p(o)), "rt_get_hierarchy_info")
         return dict(triangles=int(o[0]), nodes=int(o[2]), depth=int(o[3]), node_bytes=int(o[4]), triangle_bytes=int(o[5]),
                     build_us=int(o[6]), build_iterations=int(o[7]))
+
+    def sample_counts(self, n: int) -> np.ndarray:
+        """Per-pixel sample counts of the last adaptive render (RenderPixel's final `samp`)."""
+        out = np.zeros(n, np.uint32)
+        _check(self.lib.rt_get_sample_counts(self.h, _p(out), C.c_uint32(n)), "rt_get_sample_counts")
+        return out
 
     # ---- Render / RenderTask ----------------------------------------------------------------
     def render_task(self, cam, params, width, height, pixel_begin=0, pixel_count=None, pixel_ids=None, sample_begin=0,

@@ -105,10 +105,14 @@ struct rt_scene {
     float4 *accum = nullptr; size_t accum_cap = 0;
     uint32_t *ids = nullptr; size_t ids_cap = 0;
     float *out_stage = nullptr; size_t out_stage_cap = 0;
+    float4 *scratch = nullptr; size_t scratch_cap = 0;        // adaptive sampling: per-pixel sample colours
+    uint32_t *ad_u32 = nullptr; size_t ad_u32_cap = 0;        // adaptive sampling: nsamples + 2 x (pixel, local) lists + counter
+    uint32_t last_adaptive_pixels = 0;
     std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
     size_t tev_used = 0;
     int sm_count = 148;
     int trace_grid = 148 * 8;            // persistent grid of k_trace_wave: resident blocks of the whole chip
+    int logic_grid = 148 * 6;            // same for k_logic
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -308,6 +312,8 @@ extern "C" void rt_scene_destroy(rt_scene *sc) {
     if (sc->accum) cudaFree(sc->accum);
     if (sc->ids) cudaFree(sc->ids);
     if (sc->out_stage) cudaFree(sc->out_stage);
+    if (sc->scratch) cudaFree(sc->scratch);
+    if (sc->ad_u32) cudaFree(sc->ad_u32);
     if (sc->pool.h_counts) cudaFreeHost(sc->pool.h_counts);
     for (int k = 0; k < 4; ++k) if (sc->pool.count_ev[k]) cudaEventDestroy(sc->pool.count_ev[k]);
     sc->mem.release();
@@ -354,6 +360,8 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
         int per_sm = 0;
         CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false>, RT_TRACE_BLOCK, 0));
         sc->trace_grid = sc->sm_count * std::max(1, per_sm);
+        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logic, 128, 0));
+        sc->logic_grid = sc->sm_count * std::max(1, per_sm) * 2;
     }
     cudaStream_t st = sc->stream;
 
@@ -637,7 +645,7 @@ static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint3
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
         if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
-        k_logic<<<cdiv(std::max(1u, bound), 128), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow, gen);
+        k_logic<<<std::min(cdiv(std::max(1u, bound), 128), (uint32_t)sc->logic_grid), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow, gen);
         CKL("k_logic");
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
@@ -700,6 +708,11 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
         CK(cudaEventRecord(sc->ev1, user_stream));
         CK(cudaStreamWaitEvent(st, sc->ev1, 0));
     }
+    if ((flags & RT_FLAG_ADAPTIVE) && params->min_samples < params->max_samples) {
+        if (params->min_samples == 0) return fail(RT_ERR_ARG, "adaptive sampling needs min_samples >= 1");
+        if (flags & RT_OUT_SUM) return fail(RT_ERR_ARG, "adaptive sampling resolves per pixel; RT_OUT_SUM is not meaningful");
+        sample_count = params->min_samples;        // first loop of RenderPixel (main.cpp:237-243); the second follows below
+    }
     memset(&sc->stats, 0, sizeof(sc->stats));
     sc->tev_used = 0;
     uint64_t launches = 0;
@@ -735,6 +748,16 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
     CKR(cudaMemsetAsync(p.tcount, 0, sizeof(TraceCounters), st));
     CKR(cudaEventRecord(sc->ev0, st));
 
+    const bool adaptive = (flags & RT_FLAG_ADAPTIVE) && params->min_samples < params->max_samples;
+    const uint32_t max_s = params->max_samples;
+    uint32_t *d_nsamples = nullptr;
+    if (adaptive) {
+        rc = grow(sc, &sc->scratch, &sc->scratch_cap, (size_t)pixel_count * max_s);
+        if (rc) return done(rc);
+        rc = grow(sc, &sc->ad_u32, &sc->ad_u32_cap, 5 * (size_t)pixel_count + 4);
+        if (rc) return done(rc);
+        d_nsamples = sc->ad_u32;
+    }
     for (uint32_t p0 = 0; p0 < pixel_count; p0 += pix_per_batch) {
         const uint32_t npix = std::min(pix_per_batch, pixel_count - p0);
         for (uint32_t s0 = 0; s0 < sample_count; s0 += spp_chunk) {
@@ -746,12 +769,43 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
             gen.pixel_begin = pixel_begin; gen.pixel_local0 = p0; gen.sample_begin = sample_begin + s0; gen.jitter_scale = 0.5f; gen.enabled = 1;
             rc = run_waves(sc, prm, n_slots, flags, &launches, &gen);
             if (rc) return done(rc);
-            k_resolve<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, p0);
+            if (adaptive) k_resolve_scratch<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, sc->scratch, max_s, p0, s0);
+            else k_resolve<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, p0);
             { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_resolve failed: %s", cudaGetErrorString(e_))); }
             launches++;
         }
     }
-    k_finalize<<<cdiv(pixel_count, 128), 128, 0, st>>>(accum, pixel_count, sample_count, nullptr, flags & 3u, (float4 *)out_dev, d_ids, pixel_begin);
+    if (adaptive) {
+        // RenderPixel's second loop (main.cpp:246-258): one more sample per still-active pixel per iteration, jitter x 1.0
+        uint32_t *lists[2][2] = {{sc->ad_u32 + pixel_count, sc->ad_u32 + 2 * (size_t)pixel_count},
+                                 {sc->ad_u32 + 3 * (size_t)pixel_count, sc->ad_u32 + 4 * (size_t)pixel_count}};
+        uint32_t *d_count = sc->ad_u32 + 5 * (size_t)pixel_count;
+        k_adaptive_init<<<cdiv(pixel_count, 256), 256, 0, st>>>(pixel_count, d_ids, pixel_begin, lists[0][0], lists[0][1], d_nsamples, max_s);
+        launches++;
+        uint32_t n_active = pixel_count;
+        int cur = 0;
+        for (uint32_t samp = params->min_samples; samp < max_s && n_active > 0; ++samp) {
+            CKR(cudaMemsetAsync(d_count, 0, 4, st));
+            for (uint32_t a0 = 0; a0 < n_active; a0 += p.capacity) {   // more active pixels than pool slots: chunks
+                const uint32_t na = std::min(p.capacity, n_active - a0);
+                PrimaryGen gen;
+                memset(&gen, 0, sizeof(gen));
+                gen.cam = dcam; gen.base_seed = prm.base_seed; gen.pixel_ids = lists[cur][0] + a0; gen.n_slots = na; gen.spp = 1; gen.width = width;
+                gen.pixel_begin = 0; gen.pixel_local0 = 0; gen.sample_begin = sample_begin + samp; gen.jitter_scale = 1.0f; gen.enabled = 1;
+                rc = run_waves(sc, prm, na, flags, &launches, &gen);
+                if (rc) return done(rc);
+                k_adaptive_update<<<cdiv(na, 128), 128, 0, st>>>(p.paths.acc, na, samp, max_s, lists[cur][0] + a0, lists[cur][1] + a0, accum, sc->scratch,
+                                                                d_nsamples, lists[cur ^ 1][0], lists[cur ^ 1][1], d_count);
+                { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_adaptive_update failed: %s", cudaGetErrorString(e_))); }
+                launches++;
+            }
+            CKR(cudaMemcpyAsync(&n_active, d_count, 4, cudaMemcpyDeviceToHost, st));
+            CKR(cudaStreamSynchronize(st));
+            cur ^= 1;
+        }
+        sc->last_adaptive_pixels = pixel_count;
+    }
+    k_finalize<<<cdiv(pixel_count, 128), 128, 0, st>>>(accum, pixel_count, sample_count, d_nsamples, flags & 3u, (float4 *)out_dev, d_ids, pixel_begin);
     { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_finalize failed: %s", cudaGetErrorString(e_))); }
     launches++;
     CKR(cudaEventRecord(sc->ev1, st));
@@ -1014,5 +1068,16 @@ extern "C" int rt_rng_kat(int device, uint64_t seed, uint32_t n, uint64_t *out_h
     cudaError_t e = cudaMemcpy(out_host, d, (size_t)n * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, "rng kat failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+// Per-pixel sample counts (RenderPixel's final `samp`, main.cpp:262) of the last RT_FLAG_ADAPTIVE render on this scene.
+extern "C" int rt_get_sample_counts(rt_scene *sc, uint32_t *out_host, uint32_t n) {
+    g_err.clear();
+    if (!sc || !out_host) return fail(RT_ERR_ARG, "null argument");
+    if (n > sc->last_adaptive_pixels || !sc->ad_u32) return fail(RT_ERR_STATE, "no adaptive render of >= %u pixels on this scene", n);
+    CK(cudaSetDevice(sc->device));
+    CK(cudaMemcpyAsync(out_host, sc->ad_u32, (size_t)n * 4, cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaStreamSynchronize(sc->stream));
     return RT_OK;
 }

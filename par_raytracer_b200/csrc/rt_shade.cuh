@@ -161,11 +161,13 @@ struct ShadowQueue { float4 *o; float4 *rad; uint32_t *count; uint32_t capacity;
 #endif
 __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
                                               uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh, PrimaryGen G) {
-    uint32_t n_in = G.enabled ? G.n_slots : min(*n_in_ptr, n_in_max);
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = i < n_in;
+    const uint32_t n_in = G.enabled ? G.n_slots : min(*n_in_ptr, n_in_max);
     const uint32_t cap = P.capacity;
     const int bd = (int)prm.bounce_depth;
+    // persistent blocks, block-uniform trip count (every lane of a warp reaches the warp-aggregated pushes together)
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_in; base += gridDim.x * blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    bool active = i < n_in;
 
     uint32_t slot = 0, sp = 0;
     int iters = 0;
@@ -183,9 +185,10 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
         HitRec h = hits[i];
         f3 org;
         if (G.enabled) {
-            // wave 0: the primary ray and the fresh path state are recomputed, not streamed (rt_raygen.cuh)
+            // wave 0: the primary ray and the fresh path state are recomputed, not streamed (rt_raygen.cuh); a primary
+            // miss needs neither (the path ends with the background colour)
             slot = i;
-            primary_ray(G, i, rng, org, V);
+            if (h.tri >= 0) primary_ray(G, i, rng, org, V); else org = mk3(0, 0, 0);
             T = mk3(1.0f, 1.0f, 1.0f); iters = bd; sp = 0;
         } else {
             // every independent load of the path's state is issued before the first use
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
     // K6: compaction -- the next wave's queue holds only rays that exist
     uint32_t pos = warp_push(n_out, emit);
     if (emit) { qout.o[pos] = mk4(e_org, 0.0f); qout.d[pos] = mk4u(e_dir, slot); }
+    }
 }
 
 // ---- K7: accumulate / resolve (main.cpp:242, 262-263) -----------------------------------------------
@@ -390,7 +394,6 @@ __global__ void k_resolve(const float4 *acc, uint32_t n_pixels, uint32_t spp, fl
     accum[pixel_local0 + p] = c;
 }
 
-// per-sample colours of one batch, copied out for the adaptive loop's variance test
 __global__ void k_finalize(const float4 *accum, uint32_t n_pixels, uint32_t n_samples, const uint32_t *per_pixel_samples, uint32_t flags,
                            float4 *out, const uint32_t *pixel_ids_dev, uint32_t pixel_begin) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,6 +405,74 @@ __global__ void k_finalize(const float4 *accum, uint32_t n_pixels, uint32_t n_sa
     else { float fs = (float)ns; r = make_float4(c.x / fs, c.y / fs, c.z / fs, 1.0f); }   // main.cpp:262-263
     size_t dst = (flags & 2u) ? (size_t)(pixel_ids_dev ? pixel_ids_dev[p] : pixel_begin + p) : (size_t)p;
     out[dst] = r;
+}
+
+// ---- adaptive sampling: RenderPixel's second loop (main.cpp:245-258) ----------------------------------------
+// Phase A keeps every sample colour of the min_samples pass (the reference's scratch_buffer, main.cpp:232, 241).
+__global__ void k_resolve_scratch(const float4 *acc, uint32_t n_pixels, uint32_t spp, float4 *accum, float4 *scratch, uint32_t max_samples,
+                                  uint32_t pixel_local0, uint32_t samp0) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    uint32_t pl = pixel_local0 + p;
+    float4 c = accum[pl];
+    for (uint32_t s = 0; s < spp; ++s) {
+        float4 a = acc[(size_t)p * spp + s];
+        scratch[(size_t)pl * max_samples + samp0 + s] = a;
+        c.x += a.x; c.y += a.y; c.z += a.z;
+    }
+    accum[pl] = c;
+}
+
+// CalculateVariance + Color_Distance (main.cpp:179-186, 206-222) over the first `count` samples, same operation order
+RT_DEVICE float calc_variance(const float4 *vals, uint32_t count) {
+    float mx = 0.0f, my = 0.0f, mz = 0.0f;
+    for (uint32_t i = 0; i < count; ++i) { float4 v = vals[i]; mx += v.x; my += v.y; mz += v.z; }
+    float fc = (float)count;
+    mx = mx / fc; my = my / fc; mz = mz / fc;
+    float variance = 0.0f;
+    for (uint32_t i = 0; i < count; ++i) {
+        float4 v = vals[i];
+        float d = fabsf(v.x - mx) + fabsf(v.y - my) + fabsf(v.z - mz);
+        variance += d * d;
+    }
+    variance /= (float)(count - 1u);
+    return variance;
+}
+
+__global__ void k_adaptive_init(uint32_t n_pixels, const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t *act_pixel, uint32_t *act_local,
+                                uint32_t *nsamples, uint32_t max_samples) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pixels) return;
+    act_pixel[p] = pixel_ids ? pixel_ids[p] : pixel_begin + p;
+    act_local[p] = p;
+    nsamples[p] = max_samples;
+}
+
+// One iteration of the loop at main.cpp:246-258 for every still-active pixel: the new sample (index samp) is stored and
+// added, the variance of the samples BEFORE it decides (main.cpp:253 -- the newest sample is excluded), and a converged
+// pixel divides by samp although samp + 1 samples were summed (main.cpp:262).
+__global__ void k_adaptive_update(const float4 *acc, uint32_t n_active, uint32_t samp, uint32_t max_samples, const uint32_t *act_pixel,
+                                  const uint32_t *act_local, float4 *accum, float4 *scratch, uint32_t *nsamples, uint32_t *out_pixel,
+                                  uint32_t *out_local, uint32_t *n_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < n_active;
+    bool keep = false;
+    uint32_t pl = 0, px = 0;
+    if (active) {
+        pl = act_local[i]; px = act_pixel[i];
+        float4 a = acc[i];
+        float4 *sc = scratch + (size_t)pl * max_samples;
+        sc[samp] = a;
+        float4 c = accum[pl];
+        c.x += a.x; c.y += a.y; c.z += a.z;
+        accum[pl] = c;
+        float var = calc_variance(sc, samp);
+        const float variance_threshold = 0.01f;
+        if (var <= variance_threshold) nsamples[pl] = samp;
+        else if (samp + 1u < max_samples) keep = true;
+    }
+    uint32_t pos = warp_push(n_out, keep);
+    if (keep) { out_pixel[pos] = px; out_local[pos] = pl; }
 }
 
 // RaycastHit (raytracer.cpp:20-30) for the API: position / normal / bw / vertex0 / object from a HitRec

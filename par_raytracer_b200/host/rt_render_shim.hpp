@@ -117,8 +117,9 @@ inline void Flatten(Scene * scene, FlatScene * f) {
     d.n_lights = scene->light_count;          d.lights = (const rt_light *)scene->lights;
 }
 
-// min_samples == max_samples gives the fixed-spp mean; base_seed: see rt_params in rt_b200.h.
-inline Framebuffer RenderB200(Camera * cam, Scene * scene, u32 width, u32 height, u32 min_samples = 10, u32 max_samples = 10,
+// Defaults = Render's hard-coded adaptive 10..50 samples (main.cpp:308-309); min_samples == max_samples gives the fixed-spp
+// mean; base_seed: see rt_params in rt_b200.h.
+inline Framebuffer RenderB200(Camera * cam, Scene * scene, u32 width, u32 height, u32 min_samples = 10, u32 max_samples = 50,
                               u64 base_seed = 0x835fdd9143716fe3ULL, int device = -1, rt_counters * out_counters = NULL) {
     Framebuffer result;
     result.width = width; result.height = height; result.pixels = NULL;
@@ -153,8 +154,8 @@ inline Framebuffer RenderB200(Camera * cam, Scene * scene, u32 width, u32 height
     {
         MPI_Barrier(MPI_COMM_WORLD);                                             // main.cpp:326-333
         TIME_BLOCK("Render, sync");
-        rc = rt_render(handle, (const rt_camera *)cam, &params, width, height, NULL, start_idx, count, 0, min_samples, RT_OUT_MEAN,
-                       (float *)buffer, &counters);
+        rc = rt_render(handle, (const rt_camera *)cam, &params, width, height, NULL, start_idx, count, 0, min_samples,
+                       RT_OUT_MEAN | (min_samples < max_samples ? RT_FLAG_ADAPTIVE : 0u), (float *)buffer, &counters);
         if (rc != RT_OK) fprintf(stderr, "rt_render failed: %s\n", rt_last_error());
         MPI_Barrier(MPI_COMM_WORLD);
     }

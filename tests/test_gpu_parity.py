@@ -208,3 +208,29 @@ def test_degenerate_scenes():
         with pytest.raises(api.RtError):
             S.render_task(cam, p, 32, 24, pixel_begin=32 * 24 - 1, pixel_count=2)      # range beyond the frame
         S.close()
+
+
+def test_adaptive_sampling_against_reference(gscene):
+    """RenderPixel's second loop on the GPU (RT_FLAG_ADAPTIVE) against the reference's own adaptive render of the same
+    frame (golden). The variance test compares colours that agree to ~1e-7 relative, so a pixel whose variance sits
+    within that distance of the 0.01 threshold may stop one sample earlier or later: sample counts must match on
+    >= 99.5 % of the pixels, and colours where they match."""
+    gs, S = gscene
+    p = gs.params.copy(); p["min_samples"], p["max_samples"] = gs.adaptive_minmax
+    img, cnt = S.render_task(gs.cam, p, gs.W, gs.H, flags=api.RT_FLAG_ADAPTIVE)
+    ns = S.sample_counts(gs.W * gs.H)
+    same = ns == gs.adaptive_nsamples
+    assert same.mean() >= 0.995, f"sample counts differ on {(~same).sum()} pixels"
+    assert gs.adaptive_nsamples.min() < gs.adaptive_minmax[1], "fixture must exercise the early exit"
+    assert np.allclose(img[same], gs.adaptive_rgba[same], rtol=RTOL, atol=ATOL)
+    if same.all():
+        assert cnt["ray_count"] == gs.adaptive_counters["ray_count"]
+    # pool smaller than the number of active pixels: chunked iterations give the same result
+    import os
+    os.environ["RT_B200_POOL"] = "500"
+    try:
+        img2, _ = S.render_task(gs.cam, p, gs.W, gs.H, flags=api.RT_FLAG_ADAPTIVE)
+        ns2 = S.sample_counts(gs.W * gs.H)
+    finally:
+        del os.environ["RT_B200_POOL"]
+    assert np.array_equal(ns, ns2) and np.array_equal(bits(img), bits(img2))
