@@ -255,6 +255,16 @@ int rt_trace_primary(rt_scene *scene, const rt_camera *cam, const rt_params *par
 int rt_trace_color(rt_scene *scene, const rt_params *params, const rt_ray *rays,
                    const uint64_t *seeds, uint64_t n, float *out_rgba, rt_counters *out_counters);
 
+/* ---- WriteFramebufferImage minus the PNG (main.cpp:78-127, color.h:94-111) -------- */
+
+/* Global log-average-luma Reinhard tone map (key 0.18) + Color_Pack to RGBA8 of a W*H float4 frame that is already on the
+ * device (e.g. rt_render_device's output): the step right after Render(). out_scene_luma_host (optional) receives
+ * LogAverageLuma. Downloading the 4-byte pixels instead of the 16-byte ones is the point; stbi_write_png stays on the host. */
+int rt_tonemap_device(int device, const float *rgba_device, uint32_t width, uint32_t height, uint8_t *out_rgba8_device,
+                      float *out_scene_luma_host, void *stream);
+/* Same with host buffers (upload, tone map, download). */
+int rt_tonemap(int device, const float *rgba_host, uint32_t width, uint32_t height, uint8_t *out_rgba8_host, float *out_scene_luma);
+
 /* ---- introspection --------------------------------------------------------------- */
 int rt_get_stats(const rt_scene *scene, rt_stats *out);
 

@@ -45,6 +45,7 @@ def lib():
         L.orc_scene_create.argtypes = [C.c_void_p]
         L.orc_scene_destroy.argtypes = [C.c_void_p]
         L.orc_render.restype = C.c_double
+        L.orc_tonemap.restype = C.c_float
         _LIB = L
     return _LIB
 
@@ -178,3 +179,12 @@ def srgb_lut() -> np.ndarray:
     out = np.zeros(256, np.float32)
     lib().orc_srgb_lut(_p(out))
     return out
+
+
+def tonemap(frame: np.ndarray):
+    """(H, W, 4) float32 -> ((H, W, 4) uint8, scene_luma): LogAverageLuma + tone map + Color_Pack (main.cpp:78-127)."""
+    frame = np.ascontiguousarray(frame, np.float32)
+    h, w = frame.shape[:2]
+    out = np.zeros((h, w, 4), np.uint8)
+    luma = lib().orc_tonemap(_p(frame), C.c_uint32(w), C.c_uint32(h), _p(out))
+    return out, float(luma)

@@ -550,4 +550,21 @@ int ref_check_jitter_order(const rt_camera *c, u32 width, u32 height, u32 x, u32
     return memcmp(&a, &b, 16) == 0 && d0.ray_count == d1.ray_count;
 }
 
+// The reference's own LogAverageLuma and WriteFramebufferImage (main.cpp:78-131) on a caller-supplied frame; the PNG it
+// writes is read back with the stb_image the reference already compiles in. Returns scene_luma.
+float ref_tonemap_png(u32 width, u32 height, const float *rgba, const char *tmp_png, u8 *out_rgba8) {
+    Framebuffer fb; fb.pixels = (Vector4 *)rgba; fb.width = width; fb.height = height;
+    float luma = LogAverageLuma(&fb);
+    s32 saved = gMPI_CommRank; gMPI_CommRank = 0;
+    char *fn = strdup(tmp_png);
+    WriteFramebufferImage(&fb, fn);
+    gMPI_CommRank = saved;
+    s32 x = 0, y = 0, ch = 0;
+    u8 *img = stbi_load(fn, &x, &y, &ch, 4);
+    free(fn);
+    if (img && (u32)x == width && (u32)y == height) memcpy(out_rgba8, img, (size_t)width * height * 4);
+    if (img) stbi_image_free(img);
+    return luma;
+}
+
 } // extern "C"

@@ -42,6 +42,7 @@ class RefHarness:
         L.ref_render_seeded.restype = C.c_double
         L.ref_render_ranks.restype = C.c_double
         L.ref_check_jitter_order.restype = C.c_int
+        L.ref_tonemap_png.restype = C.c_float
         self.loaded = False
 
     # ---- scene ---------------------------------------------------------------------------
@@ -227,6 +228,16 @@ class RefHarness:
                                         C.c_uint32(pixel_count), C.c_uint32(min_samples), C.c_uint32(max_samples),
                                         C.c_uint32(threads), _p(out), _p(cnt))
         return out, cnt[0], float(sec)
+
+    def tonemap(self, frame: np.ndarray):
+        """The reference's WriteFramebufferImage on `frame` ((H, W, 4) float32): returns (RGBA8 image, scene_luma)."""
+        import tempfile
+        frame = np.ascontiguousarray(frame, np.float32)
+        h, w = frame.shape[:2]
+        out = np.zeros((h, w, 4), np.uint8)
+        path = os.path.join(tempfile.mkdtemp(prefix="ref_png_"), "out.png")
+        luma = self.lib.ref_tonemap_png(C.c_uint32(w), C.c_uint32(h), _p(frame), path.encode(), _p(out))
+        return out, float(luma)
 
     def check_jitter_order(self, cam, width, height, x, y, seed) -> bool:
         cam = np.asarray(cam, CAMERA).reshape(1)

@@ -712,6 +712,40 @@ double orc_render(const orc_scene *s, const rt_camera *cam, const rt_params *P, 
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+/* ======================================================================================== */
+/* main.cpp:78-127 LogAverageLuma + WriteFramebufferImage's tone map, color.h:94-111 Color_Luma / Color_Pack  */
+/* ======================================================================================== */
+static inline float color_luma(v4 c) { return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z; }
+
+float orc_log_average_luma(const float *rgba, uint32_t width, uint32_t height) {       /* main.cpp:78-99 */
+    float lavg = 0.0f;
+    for (uint32_t y = 0; y < height; ++y)
+        for (uint32_t x = 0; x < width; ++x) {
+            float cl = color_luma(v4_ld(rgba + 4 * ((size_t)y * width + x)));
+            if (cl > 0.0f) lavg += logf(0.01f + cl);
+        }
+    return expf(lavg / (float)(width * height));
+}
+
+float orc_tonemap(const float *rgba, uint32_t width, uint32_t height, uint8_t *out_rgba8) {   /* main.cpp:107-127 */
+    float scene_luma = orc_log_average_luma(rgba, width, height);
+    for (size_t idx = 0; idx < (size_t)width * height; ++idx) {
+        v4 c = v4_ld(rgba + 4 * idx);
+        float key_alpha = 0.18f;
+        float pixel_luma = color_luma(c);
+        float l_xy = key_alpha * pixel_luma / scene_luma;
+        float l_d = l_xy / (1.0f + l_xy);
+        float scale = l_d / pixel_luma;
+        c.x *= scale; c.y *= scale; c.z *= scale;
+        uint8_t *p = out_rgba8 + 4 * idx;                                                 /* Color_Pack, color.h:105-111 */
+        p[0] = (uint8_t)(CLAMPF(c.x, 0.0f, 1.0f) * 255.0f);
+        p[1] = (uint8_t)(CLAMPF(c.y, 0.0f, 1.0f) * 255.0f);
+        p[2] = (uint8_t)(CLAMPF(c.z, 0.0f, 1.0f) * 255.0f);
+        p[3] = (uint8_t)(CLAMPF(c.w, 0.0f, 1.0f) * 255.0f);
+    }
+    return scene_luma;
+}
+
 /* ---- function-level probes --------------------------------------------------------------- */
 void orc_rng_next_n(uint64_t seed, uint32_t n, uint64_t *out) {
     orc_rng r; orc_rng_seed(&r, seed);

@@ -28,7 +28,7 @@ RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
            "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat",
-           "rt_get_sample_counts"]
+           "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap"]
 
 
 class RtError(RuntimeError):
@@ -67,6 +67,24 @@ def rng_kat(seed: int, n: int, device: int = 0) -> np.ndarray:
     out = np.zeros(n, np.uint64)
     _check(load_library().rt_rng_kat(C.c_int(device), C.c_uint64(seed), C.c_uint32(n), _p(out)), "rt_rng_kat")
     return out
+
+
+def tonemap(frame: np.ndarray, device: int = 0):
+    """WriteFramebufferImage's tone map + Color_Pack (main.cpp:101-127) on the GPU: (H, W, 4) float32 -> (H, W, 4) uint8, scene_luma."""
+    frame = np.ascontiguousarray(frame, np.float32)
+    h, w = frame.shape[:2]
+    out = np.zeros((h, w, 4), np.uint8)
+    luma = C.c_float(0)
+    _check(load_library().rt_tonemap(C.c_int(device), _p(frame), C.c_uint32(w), C.c_uint32(h), _p(out), C.byref(luma)), "rt_tonemap")
+    return out, float(luma.value)
+
+
+def tonemap_device(frame_ptr: int, width: int, height: int, out_ptr: int, device: int = 0, stream: int = 0) -> float:
+    """Same on device buffers (e.g. torch tensors' data_ptr()): float4 frame in, RGBA8 out. Returns scene_luma."""
+    luma = C.c_float(0)
+    _check(load_library().rt_tonemap_device(C.c_int(device), C.c_void_p(frame_ptr), C.c_uint32(width), C.c_uint32(height),
+                                            C.c_void_p(out_ptr), C.byref(luma), C.c_void_p(stream)), "rt_tonemap_device")
+    return float(luma.value)
 
 
 class Scene:

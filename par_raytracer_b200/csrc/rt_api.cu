@@ -1081,3 +1081,50 @@ extern "C" int rt_get_sample_counts(rt_scene *sc, uint32_t *out_host, uint32_t n
     CK(cudaStreamSynchronize(sc->stream));
     return RT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// rt_tonemap_device / rt_tonemap: WriteFramebufferImage's tone map + Color_Pack (main.cpp:101-127) without the PNG
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_tonemap_device(int device, const float *rgba_device, uint32_t width, uint32_t height, uint8_t *out_rgba8_device,
+                                 float *out_scene_luma_host, void *stream) {
+    g_err.clear();
+    if (!rgba_device || !out_rgba8_device) return fail(RT_ERR_ARG, "null argument");
+    const uint64_t n64 = (uint64_t)width * height;
+    if (n64 == 0 || n64 > 0xFFFFFFFFull) return fail(RT_ERR_ARG, "bad frame size");
+    const uint32_t n = (uint32_t)n64;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t nb = std::min(cdiv(n, 256), 1024u);
+    double *partial; float *luma;
+    CK(cudaMalloc((void **)&partial, nb * sizeof(double) + sizeof(float)));
+    luma = (float *)(partial + nb);
+    k_luma_partial<<<nb, 256, 0, st>>>((const float4 *)rgba_device, n, partial);
+    k_luma_final<<<1, 32, 0, st>>>(partial, nb, n, luma);
+    k_tonemap_pack<<<cdiv(n, 256), 256, 0, st>>>((const float4 *)rgba_device, n, luma, (uchar4 *)out_rgba8_device);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && out_scene_luma_host) e = cudaMemcpyAsync(out_scene_luma_host, luma, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(partial);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "tone map failed: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
+extern "C" int rt_tonemap(int device, const float *rgba_host, uint32_t width, uint32_t height, uint8_t *out_rgba8_host, float *out_scene_luma) {
+    g_err.clear();
+    if (!rgba_host || !out_rgba8_host) return fail(RT_ERR_ARG, "null argument");
+    const size_t n = (size_t)width * height;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    float *d_in; uint8_t *d_out;
+    CK(cudaMalloc((void **)&d_in, std::max<size_t>(1, n) * 16));
+    if (cudaMalloc((void **)&d_out, std::max<size_t>(1, n) * 4) != cudaSuccess) { cudaFree(d_in); return fail(RT_ERR_NOMEM, "out of device memory"); }
+    int rc = RT_OK;
+    if (cudaMemcpy(d_in, rgba_host, n * 16, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(RT_ERR_CUDA, "upload failed");
+    if (rc == RT_OK) rc = rt_tonemap_device(device, d_in, width, height, d_out, out_scene_luma, nullptr);
+    if (rc == RT_OK && cudaMemcpy(out_rgba8_host, d_out, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(RT_ERR_CUDA, "download failed");
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}

@@ -61,6 +61,8 @@ class GoldenScene:
         self.adaptive_rgba = z["adaptive_rgba"]
         self.adaptive_nsamples = z["adaptive_nsamples"]
         self.adaptive_counters = np.frombuffer(z["adaptive_counters"].tobytes(), COUNTERS)[0]
+        self.tonemap_rgba8 = z["tonemap_rgba8"]
+        self.tonemap_luma = float(z["tonemap_luma"][0])
 
 
 @pytest.fixture(scope="session", params=["spheres", "heightfield"])

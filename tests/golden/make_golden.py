@@ -143,6 +143,8 @@ def scene_vectors(R, name, sd, W, H, params, lights=None, n_random=4000, n_color
     # sample-range split: samples [2, 2 + render_spp) as raw sums
     img2, _, _, _ = R.render_seeded(cam, W, H, None, 0, W * H, 2, render_spp, render_spp, seed, sum_only=True, threads=8)
     out["render_sum_from2"] = img2
+    tm, tl = R.tonemap(img.reshape(H, W, 4))                     # the reference's WriteFramebufferImage on its own frame
+    out["tonemap_rgba8"] = tm; out["tonemap_luma"] = np.array([tl], np.float32)
     a0, a1 = adaptive
     imga, nsa, acnt, _ = R.render_seeded(cam, W, H, None, 0, W * H, 0, a0, a1, seed, threads=8)
     out["adaptive_minmax"] = np.array([a0, a1], np.uint32)

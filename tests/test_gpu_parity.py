@@ -234,3 +234,26 @@ def test_adaptive_sampling_against_reference(gscene):
     finally:
         del os.environ["RT_B200_POOL"]
     assert np.array_equal(ns, ns2) and np.array_equal(bits(img), bits(img2))
+
+
+def test_tonemap_on_device(gscene):
+    """GPU tone map + RGBA8 pack vs the PNG the reference wrote for the same float frame. The reference sums logf in 32-bit
+    scan order; the GPU reduces in double, and logf/expf are CUDA's: scene_luma within 2e-6 relative, and because the pack
+    truncates (u8)(x * 255) a value sitting on a code boundary may land one code lower or higher (<= 1 % of the channels)."""
+    gs, S = gscene
+    frame = gs.render_rgba.reshape(gs.H, gs.W, 4)
+    img, luma = api.tonemap(frame)
+    assert abs(luma - gs.tonemap_luma) <= 2e-6 * gs.tonemap_luma
+    d = np.abs(img.astype(np.int32) - gs.tonemap_rgba8.astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() <= 0.01
+    assert np.all(img[..., 3] == 255)
+    # chained on the device: render -> tone map -> 4-byte pixels
+    import torch
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
+    f = torch.zeros((gs.W * gs.H, 4), dtype=torch.float32, device="cuda")
+    out8 = torch.zeros((gs.W * gs.H, 4), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    S.render_device(gs.cam, p, gs.W, gs.H, f.data_ptr(), sample_count=gs.render_spp, flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME, stream=st)
+    api.tonemap_device(f.data_ptr(), gs.W, gs.H, out8.data_ptr(), stream=st)
+    d2 = np.abs(out8.cpu().numpy().reshape(gs.H, gs.W, 4).astype(np.int32) - gs.tonemap_rgba8.astype(np.int32))
+    assert d2.max() <= 1 and (d2 != 0).mean() <= 0.01
