@@ -110,6 +110,7 @@ struct rt_scene {
     uint32_t last_adaptive_pixels = 0;
     std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
     size_t tev_used = 0;
+    std::vector<std::pair<uint64_t, uint64_t>> wave_log;   // (closest, shadow) rays per issued wave, aligned with tev (RT_B200_WAVE_LOG=1)
     int sm_count = 148;
     int trace_grid = 148 * 8;            // persistent grid of k_trace_wave: resident blocks of the whole chip
     int logic_grid = 148 * 6;            // same for k_logic
@@ -580,21 +581,33 @@ static int wave_event(rt_scene *sc, bool on) {
 
 // sums the per-wave event intervals recorded since tev_used was reset (stream must be idle)
 static int collect_wave_times(rt_scene *sc) {
+    const bool log = getenv("RT_B200_WAVE_LOG") != nullptr;
     for (size_t i = 0; i + 3 < sc->tev_used; i += 4) {
         float a = 0, b = 0, c = 0;
         CK(cudaEventElapsedTime(&a, sc->tev[i], sc->tev[i + 1]));
         CK(cudaEventElapsedTime(&b, sc->tev[i + 1], sc->tev[i + 2]));
         CK(cudaEventElapsedTime(&c, sc->tev[i + 2], sc->tev[i + 3]));
         sc->stats.trace_ms += a; sc->stats.logic_ms += b; sc->stats.shadow_ms += c;
+        if (log && i / 4 < sc->wave_log.size()) {
+            auto &wl = sc->wave_log[i / 4];
+            fprintf(stderr, "[wave %3zu] closest %9llu shadow %9llu  trace %7.3f ms (%6.0f Mrays/s)  logic %7.3f ms\n", i / 4, (unsigned long long)wl.first,
+                    (unsigned long long)wl.second, a, a > 0 ? (wl.first + wl.second) / a / 1e3 : 0.0, b);
+        }
     }
     sc->tev_used = 0;
+    sc->wave_log.clear();
     return RT_OK;
 }
 
-static uint32_t fetch_min_knob() {
-    static uint32_t v = 0;
-    if (!v) { const char *e = getenv("RT_B200_FETCH_MIN"); v = e ? (uint32_t)atoi(e) : RT_FETCH_MIN; if (v < 1 || v > 32) v = RT_FETCH_MIN; }
-    return v;
+static uint32_t env_knob(const char *name, uint32_t dflt) {
+    const char *e = getenv(name);
+    uint32_t v = e ? (uint32_t)atoi(e) : dflt;
+    return (v < 1 || v > 32) ? dflt : v;
+}
+static void set_fetch_knobs(WaveQueues &w) {
+    static uint32_t a = 0, b = 0, c = 0;
+    if (!a) { a = env_knob("RT_B200_FETCH_MIN", RT_FETCH_MIN); b = env_knob("RT_B200_FETCH_PRIMARY", RT_FETCH_MIN); c = env_knob("RT_B200_FETCH_SHADOW", RT_FETCH_MIN); }
+    w.fetch_min = a; w.fetch_min_primary = b; w.fetch_min_shadow = c;
 }
 
 static WaveQueues wave_queues(rt_scene *sc, int cur, uint32_t n_closest_max) {
@@ -603,7 +616,7 @@ static WaveQueues wave_queues(rt_scene *sc, int cur, uint32_t n_closest_max) {
     w.closest = p.q[cur]; w.n_closest = p.counts + cur; w.closest_max = n_closest_max; w.hits = p.hits;
     w.shadow_o = p.shadow.o; w.shadow_dir = nullptr; w.rad = p.shadow.rad; w.n_shadow = p.shadow.count; w.shadow_stride = p.shadow.capacity;
     w.n_lights = sc->n_lights; w.acc = p.paths.acc; w.acc_extra = p.acc_extra; w.next = p.next;
-    w.fetch_min = fetch_min_knob();
+    set_fetch_knobs(w);
     return w;
 }
 
@@ -669,11 +682,13 @@ static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint3
         sc->stats.closest_rays += c_in;
         sc->stats.shadow_rays += sh_in;
         sc->stats.waves += 1;
+        if (timed) sc->wave_log.push_back(std::make_pair((uint64_t)c_in, sh_in));
         c_in = c_out; sh_in = sh_out;
         bound = c_out;                                  // queue sizes never grow: every live path emits at most one ray per wave
         if (c_out == 0 && sh_out == 0) break;           // the wave already in flight finds empty queues and does nothing
     }
     (void)in_closest;
+    if (timed) sc->wave_log.push_back(std::make_pair((uint64_t)0, (uint64_t)0));      // the run-ahead wave that found empty queues
     if (L > 1) {
         k_fold_light_acc<<<cdiv(n_first, 256), 256, 0, st>>>(p.paths.acc, p.acc_extra, n_first, p.shadow.capacity, L - 1);
         CKL("k_fold_light_acc");
@@ -886,7 +901,7 @@ extern "C" int rt_trace_rays(rt_scene *sc, const rt_params *params, const rt_ray
         WaveQueues w;
         memset(&w, 0, sizeof(w));
         w.next = cnt + 1; w.hits = hits; w.acc = acc; w.acc_extra = acc; w.rad = rad; w.shadow_o = q.o; w.shadow_dir = q.d; w.closest = q;
-        w.n_shadow = cnt; w.shadow_stride = cap; w.fetch_min = fetch_min_knob();
+        w.n_shadow = cnt; w.shadow_stride = cap; set_fetch_knobs(w);
         int rc = RT_OK;
         if (mode == RT_TRACE_ANY) {
             k_rays_to_shadow_queue<<<cdiv(m, 256), 256, 0, st>>>(d_rays, m, q.o, q.d, rad, acc, cnt);

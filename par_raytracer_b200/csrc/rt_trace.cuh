@@ -121,7 +121,9 @@ struct WaveQueues {
     float4 *acc;                   // light 0 adds into the path accumulator ...
     float4 *acc_extra;             // ... light l >= 1 into acc_extra[(l - 1) * shadow_stride + slot] (single writer each: no atomics)
     uint32_t *next;                // work counter, zero before launch
-    uint32_t fetch_min;            // refill the warp once this many lanes are idle (32 = only when all are)
+    uint32_t fetch_min;            // refill the warp once this many lanes are idle (32 = only when all are): bounce rays
+    uint32_t fetch_min_primary;    // same while the work counter is still inside the primary rays of wave 0
+    uint32_t fetch_min_shadow;     // same inside the shadow-ray region
 };
 
 template <bool COUNT>
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
     unsigned long long n_sph = 0, n_clu = 0;
 
     bool live = false, exhausted = false;
+    uint32_t fetch_min = G.enabled ? W.fetch_min_primary : W.fetch_min;
     RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
     float inv_dd = 0.0f, dist_sq = -1.0f, slack = 0.0f;
     HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
@@ -145,11 +148,12 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
     while (true) {
         // ---- warp-cooperative fetch ----
         uint32_t idle = __ballot_sync(FULL, !live);
-        if (!exhausted && (idle == FULL || __popc(idle) >= W.fetch_min)) {
+        if (!exhausted && (idle == FULL || __popc(idle) >= fetch_min)) {
             uint32_t n_idle = __popc(idle), base = 0;
             if (lane == 0) base = atomicAdd(W.next, n_idle);
             base = __shfl_sync(FULL, base, 0);
             if (base + n_idle >= total) exhausted = true;
+            if (base + n_idle >= nC) fetch_min = W.fetch_min_shadow;      // warp-uniform: the counter has moved on to shadow rays
             if (!live) {
                 uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
                 if (idx < total) {

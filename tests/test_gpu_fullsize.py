@@ -47,3 +47,66 @@ def test_config2_full_size_properties():
     hb, _ = S.trace_rays(p, rays, api.RT_TRACE_BRUTE)
     assert hits.tobytes() == hb.tobytes()
     S.close()
+
+
+def test_config3_one_million_textured_triangles():
+    """BASELINE config 3 at full size: 1,048,352-triangle height field in 529 OBJ-style groups, 8 materials with diffuse /
+    ambient maps, bump maps and an alpha mask, 1920x1080, 128 spp."""
+    sd = scenes.heightfield_scene(724, 724, block=32, size=400.0, amp=20.0, textured=True, tex_size=512)
+    assert sd.n_triangles == 2 * 724 * 724 and sd.tangents is not None
+    S = api.Scene(sd)
+    W, H, spp = 1920, 1080, 128
+    h = sd.camera_hint
+    cam = types.make_camera(h["fov"], W, H, h["position"], h["facing"])
+    p = types.default_params(spp=spp)
+    img, cnt = S.render(cam, p, W, H)
+    flat = img.reshape(-1, 4)
+    assert np.all(np.isfinite(flat)) and np.all(flat[:, :3] >= 0) and np.all(flat[:, 3] == 1.0)
+    assert W * H * spp <= cnt["ray_count"] <= 16 * W * H * spp
+    # oracle on 150 pixels at the full 128 spp (the reference scans whole 2,048-triangle groups: ~0.05 Mrays/s/16 cores)
+    ids = np.arange(977, W * H, W * H // 150, dtype=np.uint32)[:150]
+    O = oracle.OracleScene(sd)
+    ref, _, cnt_o, _ = O.render(cam, p, W, H, pixel_ids=ids, threads=16)
+    sub, cnt_s = S.render_task(cam, p, W, H, pixel_ids=ids)
+    assert cnt_s["ray_count"] == cnt_o["ray_count"]
+    assert np.allclose(sub, ref, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(bits(sub), bits(flat[ids]))
+    # alpha-masked / bump-mapped / translucent-free materials all occur among the primary hits
+    rays, hits = S.trace_primary(cam, p, W, H, pixel_ids=ids, sample_count=4)
+    mats = sd.group_material[sd.sphere_group[hits["object"][hits["hit"] == 1]]]
+    assert len(np.unique(mats)) >= 6
+    S.close()
+
+
+def test_config4_ten_million_triangles_tile_of_a_4k_frame():
+    """BASELINE config 4 at full size: 9,999,392 triangles (4,900 groups x 2,048), 3840x2160, 256 spp. One rank's share of an
+    8-way interleaved tile partition is rendered at the full sample count; pruning is checked against brute force."""
+    sd = scenes.heightfield_scene(2236, 2236, block=32, size=400.0, amp=20.0, textured=False)
+    assert 9_900_000 < sd.n_triangles < 10_100_000 and sd.n_groups == 4900
+    S = api.Scene(sd)
+    info = S.hierarchy_info()
+    assert info["triangles"] == sd.n_triangles and info["depth"] <= 62
+    W, H, spp = 3840, 2160, 256
+    h = sd.camera_hint
+    cam = types.make_camera(h["fov"], W, H, h["position"], h["facing"])
+    p = types.default_params(spp=spp)
+    tiles = dist.tile_partition(W, H, 3, 8, 32)
+    assert len(tiles) in range(W * H // 8 - 32 * 32 * 8, W * H // 8 + 32 * 32 * 8)
+    full = tiles[: 1005 * 1024].reshape(1005, 1024)          # rank 3's 1005 complete 32x32 tiles (tile rows 0..66)
+    part = full[::25][:40].reshape(-1).copy()                # 40 of them, spread over the frame: 10.5 M samples at 256 spp
+    img, cnt = S.render_task(cam, p, W, H, pixel_ids=part)
+    assert np.all(np.isfinite(img)) and np.all(img[:, :3] >= 0) and np.all(img[:, 3] == 1.0)
+    assert len(part) * spp <= cnt["ray_count"] <= 16 * len(part) * spp
+    again, cnt2 = S.render_task(cam, p, W, H, pixel_ids=part[::-1].copy())
+    assert np.array_equal(bits(again[::-1]), bits(img)) and cnt2["ray_count"] == cnt["ray_count"]   # order of the list is irrelevant
+    # 12 pixels against the oracle at the full 256 spp
+    ids = part[:: len(part) // 12][:12]
+    O = oracle.OracleScene(sd)
+    ref, _, cnt_o, _ = O.render(cam, p, W, H, pixel_ids=ids, threads=16)
+    sub, cnt_s = S.render_task(cam, p, W, H, pixel_ids=ids)
+    assert cnt_s["ray_count"] == cnt_o["ray_count"] and np.allclose(sub, ref, rtol=1e-5, atol=1e-6)
+    # hierarchy == brute force over all 10 M triangles for 1,500 primary rays
+    rays, hits = S.trace_primary(cam, p, W, H, pixel_ids=part[::27][:1500], sample_count=1)
+    hb, _ = S.trace_rays(p, rays, api.RT_TRACE_BRUTE)
+    assert hits.tobytes() == hb.tobytes() and hits["hit"].mean() > 0.5
+    S.close()
