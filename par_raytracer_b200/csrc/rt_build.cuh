@@ -474,10 +474,12 @@ __global__ void k_gather(GatherInput in, const uint32_t *sorted_tri, const uint3
     const float *t2 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 2];
     tri_uv[2 * (size_t)dst + 0] = make_float4(t0[0], t0[1], t1[0], t1[1]);
     tri_uv[2 * (size_t)dst + 1] = make_float4(t2[0], t2[1], __int_as_float(in.group_material[g]), 0.0f);
+    f3 gn = normalize3(n);                                    // RaycastHit::normal (raytracer.cpp:122): a per-triangle constant
+    const float gnk[3] = {gn.x, gn.y, gn.z};
     for (int k = 0; k < 3; ++k) {
         uint32_t ni = in.idx_n[3 * (size_t)j + k];
         f3 nn = ld3(in.normals, ni);
-        tri_nrm[3 * (size_t)dst + k] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+        tri_nrm[3 * (size_t)dst + k] = make_float4(nn.x, nn.y, nn.z, gnk[k]);
         if (tri_tan) {
             f3 tt = ld3(in.tangents, ni);
             tri_tan[3 * (size_t)dst + k] = make_float4(tt.x, tt.y, tt.z, 0.0f);

@@ -96,7 +96,7 @@ struct DevScene {
     const TriRec *tris;
     const uint32_t *tri_rank;      // tie-break rank: position in the reference's leaf visit order
     const float4 *tri_uv;          // 2 per triangle: (u0 v0 u1 v1) (u2 v2 material_bits -)
-    const float4 *tri_nrm;         // 3 per triangle: vertex normals
+    const float4 *tri_nrm;         // 3 per triangle: vertex normals; the three w's hold Normalize(Cross(ab, ac)) (raytracer.cpp:122)
     const float4 *tri_tan;         // 3 per triangle: vertex tangents (NULL when no bump map)
     const uint32_t *tri_vertex0;   // RaycastHit::vertex0 (raytracer.cpp:147)
     const int32_t *tri_object;     // RaycastHit::object as sphere index (raytracer.cpp:148)

@@ -29,6 +29,16 @@ struct PrimaryGen {
     uint32_t enabled;               // 0: rays and path state come from the queues
 };
 
+// generator state of slot s after its two jitter draws (what primary_ray leaves in r)
+RT_DEVICE void primary_rng(const PrimaryGen &g, uint32_t s, PathRng &r) {
+    uint32_t pl = g.pixel_local0 + s / g.spp;
+    uint32_t samp = g.sample_begin + s % g.spp;
+    uint32_t pixel = g.pixel_ids ? g.pixel_ids[pl] : g.pixel_begin + pl;
+    rng_seed(r, sample_seed(g.base_seed, pixel, samp));
+    (void)rng_next(r);
+    (void)rng_next(r);
+}
+
 RT_DEVICE void primary_ray(const PrimaryGen &g, uint32_t s, PathRng &r, f3 &org, f3 &dir) {
     uint32_t pl = g.pixel_local0 + s / g.spp;
     uint32_t samp = g.sample_begin + s % g.spp;

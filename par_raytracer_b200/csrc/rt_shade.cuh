@@ -148,7 +148,7 @@ RT_DEVICE float fresnel_amount(float ior_exit, float ior_enter, f3 normal, f3 in
 #ifdef RT_PHONG_POW_F64
 RT_DEVICE float phong_pow(float x, float e) { return (float)pow((double)x, (double)e); }
 #else
-RT_DEVICE float phong_pow(float x, float e) { return powf(x, e); }
+RT_DEVICE float phong_pow(float x, float e) { return (x == 0.0f && e > 0.0f) ? 0.0f : powf(x, e); }   // pow(+0, e > 0) = +0: skip the call
 #endif
 
 // One sub-queue per light (light l owns entries [l * capacity, (l + 1) * capacity) and count[l]): a path has at most one
@@ -188,7 +188,13 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             // wave 0: the primary ray and the fresh path state are recomputed, not streamed (rt_raygen.cuh); a primary
             // miss needs neither (the path ends with the background colour)
             slot = i;
-            if (h.tri >= 0) primary_ray(G, i, rng, org, V); else org = mk3(0, 0, 0);
+            if (h.tri >= 0) {
+                // the trace kernel left the direction it generated in the queue (hits only); the origin is the camera's;
+                // the generator state after the two jitter draws is re-derived (cheaper than streaming it)
+                V = mk3(qin.d[i]);
+                org = mk3(G.cam.pos[0], G.cam.pos[1], G.cam.pos[2]);
+                primary_rng(G, i, rng);
+            } else org = mk3(0, 0, 0);
             T = mk3(1.0f, 1.0f, 1.0f); iters = bd; sp = 0;
         } else {
             // every independent load of the path's state is issued before the first use
@@ -208,14 +214,12 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
         if (h.tri < 0) {
             acc = acc + T * mk3(prm.bg[0], prm.bg[1], prm.bg[2]);          // raytracer.cpp:573-575
         } else {
-            const float4 *tp = reinterpret_cast<const float4 *>(S.tris + h.tri);
-            float4 r0 = __ldg(tp);
             float4 ua = __ldg(S.tri_uv + 2 * (size_t)h.tri), ub = __ldg(S.tri_uv + 2 * (size_t)h.tri + 1);
             const float4 *np = S.tri_nrm + 3 * (size_t)h.tri;
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             f3 ob = org + V * prm.ray_bias;                                  // raytracer.cpp:163
             f3 position = ob + V * h.t;                                      // raytracer.cpp:121
-            f3 gn = normalize3(mk3(r0.x, r0.y, r0.z));                        // raytracer.cpp:122
+            f3 gn = mk3(n0.w, n1.w, n2.w);                                   // raytracer.cpp:122, normalised once at build time
             hit_p = position + gn * prm.ray_bias;                            // raytracer.cpp:425
             int mat_id = __float_as_int(ub.z);
             DevMaterial M = S.materials[mat_id];

@@ -33,6 +33,7 @@ struct HitRec {                // 16 B per ray
 
 struct TraceCounters { unsigned long long sphere_checks, cluster_checks; };
 
+RT_DEVICE float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RT_DEVICE float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // culling only: 1 MUFU
 
 // Conservative test of a ray against one child bound = (sphere fattened by `slack`) INTERSECT (slab fattened by `slack`).
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                     c.o = mk3(o4) + dir * bias;                      // raytracer.cpp:163
                     f3 q = c.o + dir;
                     c.qp = c.o - q;
-                    inv_dd = 1.0f / __fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x));
+                    inv_dd = approx_rcp(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x)));   // culling only
                     slack = RT_CULL_SLACK * (fabsf(c.o.x) + fabsf(c.o.y) + fabsf(c.o.z) + S.cull_bound);
                     best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1; best_rank = 0xFFFFFFFFu;   // raytracer.cpp:166
                     cur = S.root; sp = 0;
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
             if (done) {
                 if (kind == 0) {
                     W.hits[out_idx] = best;
+                    if (G.enabled && best.tri >= 0) W.closest.d[out_idx] = mk4(c.d, 0.0f);   // wave 0: the shading step reads the direction back
                 } else {
                     bool lit = best.tri < 0 || (kind == 2 && best.t * best.t <= dist_sq);   // raytracer.cpp:385 / 395-396
                     if (lit) {
