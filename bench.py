@@ -43,6 +43,20 @@ def b_ray(n_tris: int) -> int:
     return 64 + 32 + 32 * math.ceil(math.log2(max(2.0, n_tris / 4.0))) + 144 + 88
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu pass (profiles/r1_traffic_per_kernel.json: dram__bytes_read.sum +
+    dram__bytes_write.sum over every launch of one config-2 frame), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic_per_kernel.json")
+    try:
+        k = json.load(open(p))["kernels"]
+        for name, v in k.items():
+            if name.startswith(kernel):
+                return float(v["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -322,10 +336,11 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": int(cam_h.nbytes + par_h.nbytes), "d2h_bytes_per_step": int(WIDTH * HEIGHT * 16),
                     "note": "rt_render_device + pinned-host download of the finished frame each step; the scene stays resident like the reference's loaded Scene"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic("k_trace_wave") if world == 1 else None,
                          "kernel": "k_trace_wave", "bytes_per_ray": bytes_per_ray, "rays_timed": traced, "kernel_ms": trace_ms,
-                         "launches_timed": waves,
-                         "peak_source": peak_src,
+                         "waves_timed": waves,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": traced * bytes_per_ray / max(1, waves),
+                         "note": "achieved counts SURVEY 8(d)'s algorithmic bytes; the 3.9 MB scene is L2-resident, so measured DRAM traffic (41.8 B/ray) is far BELOW the algorithmic 776 B/ray and frac can exceed 1: the kernel is instruction-issue bound (ncu: 73-87 % issue slots busy, DRAM < 10 %)",
                          "whole_step_frac": value * 1e6 / world * bytes_per_ray / (peak * 1e9)},
         }
         if cpu is not None:
