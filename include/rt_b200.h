@@ -255,6 +255,15 @@ int rt_trace_primary(rt_scene *scene, const rt_camera *cam, const rt_params *par
 int rt_trace_color(rt_scene *scene, const rt_params *params, const rt_ray *rays,
                    const uint64_t *seeds, uint64_t n, float *out_rgba, rt_counters *out_counters);
 
+/* ---- BuildHierarchy (bsphere.cpp:379-444) ------------------------------------------ */
+
+/* The reference's OWN hierarchy over mesh groups -- leaf sphere per group (EigenSphere + Ritter_Iterative), greedy merge of
+ * the pair with the smallest parent radius, pre-order flattening -- built on the GPU with bit-identical output (the host
+ * build is O(groups^3): ~3 min at 5,000 groups). Fills out_spheres / out_sphere_group (2 * n_groups - 1 entries) in the
+ * layout rt_scene_desc.spheres / sphere_group expects. n_groups <= 65535, no empty group. */
+int rt_build_group_hierarchy(int device, const float *positions, uint32_t n_positions, uint32_t n_groups, const uint32_t *group_first,
+                             const uint32_t *idx_positions, rt_bsphere *out_spheres, int32_t *out_sphere_group, uint32_t *out_count);
+
 /* ---- WriteFramebufferImage minus the PNG (main.cpp:78-127, color.h:94-111) -------- */
 
 /* Global log-average-luma Reinhard tone map (key 0.18) + Color_Pack to RGBA8 of a W*H float4 frame that is already on the

@@ -188,3 +188,13 @@ def tonemap(frame: np.ndarray):
     out = np.zeros((h, w, 4), np.uint8)
     luma = lib().orc_tonemap(_p(frame), C.c_uint32(w), C.c_uint32(h), _p(out))
     return out, float(luma)
+
+
+def build_hierarchy(scene: SceneData):
+    """BuildHierarchy (bsphere.cpp:379-444) restated: returns (spheres BSPHERE array, sphere_group) for the scene's groups."""
+    from par_raytracer_b200.types import BSPHERE
+    G = scene.n_groups
+    spheres = np.zeros(max(1, 2 * G - 1), BSPHERE); sg = np.zeros(max(1, 2 * G - 1), np.int32)
+    lib().orc_build_hierarchy.restype = C.c_uint32
+    n = lib().orc_build_hierarchy(_p(scene.positions), C.c_uint32(G), _p(scene.group_first), _p(scene.idx_positions), _p(spheres), _p(sg))
+    return spheres[:n], sg[:n]

@@ -746,6 +746,210 @@ float orc_tonemap(const float *rgba, uint32_t width, uint32_t height, uint8_t *o
     return scene_luma;
 }
 
+/* ======================================================================================== */
+/* bsphere.cpp:8-444 BuildHierarchy: leaf spheres (EigenSphere + Ritter_Iterative), greedy   */
+/* min-radius agglomeration, pre-order flattening. Restated on flat arrays; float order kept. */
+/* ======================================================================================== */
+typedef struct { v3 c; float r; } sph;
+typedef struct { float e[9]; } m33;                               /* mathlib.h:540-599, row-major e[i*3+j] */
+
+static m33 m33_identity(void) { m33 m = { { 1, 0, 0, 0, 1, 0, 0, 0, 1 } }; return m; }
+static m33 m33_mul(m33 a, m33 b) {                                /* mathlib.h:652-694: (a0*b0 + a1*b1) + a2*b2 */
+    m33 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            r.e[i * 3 + j] = a.e[i * 3 + 0] * b.e[0 * 3 + j] + a.e[i * 3 + 1] * b.e[1 * 3 + j] + a.e[i * 3 + 2] * b.e[2 * 3 + j];
+    return r;
+}
+static m33 m33_transpose(m33 m) {
+    m33 r;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.e[i * 3 + j] = m.e[j * 3 + i];
+    return r;
+}
+
+static void update_sphere_with_point(sph *s, v3 p) {             /* bsphere.cpp:14-26 */
+    v3 pc = v3_sub(p, s->c);
+    float sq = v3_dot(pc, pc);
+    if (sq > (s->r * s->r)) {
+        float dist = sqrtf(sq);
+        float nr = (s->r + dist) * 0.5f + 1e-2;                   /* double constant: float + double -> float */
+        float k = (nr - s->r) / dist;
+        s->r = nr;
+        s->c = v3_add(s->c, v3_scale(pc, k));
+    }
+}
+
+static m33 covariance_matrix(const v3 *pts, uint32_t n) {         /* bsphere.cpp:45-81 (m(2,1) is never set: sic) */
+    float inv = 1.0f / (float)n;
+    v3 c = v3_make(0, 0, 0);
+    float e00 = 0, e11 = 0, e22 = 0, e01 = 0, e02 = 0, e12 = 0;
+    for (uint32_t i = 0; i < n; ++i) c = v3_add(c, pts[i]);
+    c = v3_scale(c, inv);
+    for (uint32_t i = 0; i < n; ++i) {
+        v3 p = v3_sub(pts[i], c);
+        e00 += p.x * p.x; e11 += p.y * p.y; e22 += p.z * p.z;
+        e01 += p.x * p.y; e02 += p.x * p.z; e12 += p.y * p.z;
+    }
+    m33 m; memset(&m, 0, sizeof(m));
+    m.e[0] = e00 * inv; m.e[4] = e11 * inv; m.e[8] = e22 * inv;
+    m.e[1] = m.e[3] = e01 * inv;
+    m.e[2] = m.e[6] = e02 * inv;
+    m.e[5] = e12 * inv;
+    return m;
+}
+
+static void sym_schur2(m33 m, uint32_t p, uint32_t q, float *c, float *s) {   /* bsphere.cpp:83-102 */
+    const float epsilon = 0.0001f;
+    if (fabsf(m.e[p * 3 + q]) > epsilon) {
+        float r = (m.e[q * 3 + q] - m.e[p * 3 + p]) / (2.0f * m.e[p * 3 + q]);
+        float t;
+        if (r >= 0.0f) t = 1.0f / (r + sqrtf(1.0f + r * r));
+        else t = -1.0f / (-r + sqrtf(1.0f + r * r));
+        *c = 1.0f / sqrtf(1.0f + t * t);
+        *s = (*c) * t;
+    } else { *c = 1.0f; *s = 0.0f; }
+}
+
+static void jacobi(m33 *a, m33 *v) {                              /* bsphere.cpp:104-154 */
+    float prevoff = 0.0f, c, s;
+    *v = m33_identity();
+    for (uint32_t n = 0; n < 50; ++n) {
+        uint32_t p = 0, q = 1;
+        for (uint32_t i = 0; i < 3; ++i)
+            for (uint32_t j = 0; j < 3; ++j)
+                if (i != j && fabsf(a->e[i * 3 + j]) > fabsf(a->e[p * 3 + q])) { p = i; q = j; }
+        sym_schur2(*a, p, q, &c, &s);
+        m33 J = m33_identity();
+        J.e[p * 3 + p] = c; J.e[p * 3 + q] = s; J.e[q * 3 + p] = -s; J.e[q * 3 + q] = c;
+        *v = m33_mul(*v, J);
+        *a = m33_mul(m33_mul(m33_transpose(J), *a), J);
+        float off = 0.0f;
+        for (uint32_t i = 0; i < 3; ++i)
+            for (uint32_t j = 0; j < 3; ++j)
+                if (i != j) off += a->e[i * 3 + j] * a->e[i * 3 + j];
+        if (n > 2 && off >= prevoff) return;
+        prevoff = off;
+    }
+}
+
+static sph eigen_sphere(const v3 *pts, uint32_t n) {              /* bsphere.cpp:156-195 */
+    m33 m = covariance_matrix(pts, n), v;
+    jacobi(&m, &v);
+    uint32_t max_c = 0;
+    float max_e = fabsf(m.e[0]);
+    if (fabsf(m.e[4]) > max_e) { max_c = 1; max_e = fabsf(m.e[4]); }
+    if (fabsf(m.e[8]) > max_e) { max_c = 2; max_e = fabsf(m.e[8]); }
+    v3 e = v3_make(v.e[0 * 3 + max_c], v.e[1 * 3 + max_c], v.e[2 * 3 + max_c]);
+    uint32_t imin = 0, imax = 0;                                  /* bsphere.cpp:28-43 */
+    float minp = FLT_MAX, maxp = -FLT_MAX;
+    for (uint32_t i = 0; i < n; ++i) {
+        float proj = v3_dot(pts[i], e);
+        if (proj < minp) { imin = i; minp = proj; }
+        if (proj > maxp) { imax = i; maxp = proj; }
+    }
+    v3 a = pts[imin], b = pts[imax];
+    sph r;
+    r.c = v3_scale(v3_add(a, b), 0.5f);
+    v3 d = v3_sub(a, b);
+    r.r = sqrtf(v3_dot(d, d)) * 0.5f;
+    for (uint32_t i = 0; i < n; ++i) update_sphere_with_point(&r, pts[i]);
+    return r;
+}
+
+static sph ritter_iterative(sph s, v3 *pts, uint32_t n) {         /* bsphere.cpp:197-230 (shuffles pts in place) */
+    orc_rng rng;
+    orc_rng_seed(&rng, 0x201701260526ull);
+    sph s2 = s;
+    for (uint32_t k = 0; k < 16; ++k) {
+        s2.r *= 0.9f;
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t remaining = n - i - 1;
+            if (remaining) {
+                uint32_t j = (uint32_t)orc_rng_next(&rng) % remaining;
+                j += i + 1;
+                v3 tmp = pts[i]; pts[i] = pts[j]; pts[j] = tmp;
+            }
+            update_sphere_with_point(&s2, pts[i]);
+        }
+        if (s2.r < s.r) s = s2;
+    }
+    for (uint32_t i = 0; i < n; ++i) update_sphere_with_point(&s, pts[i]);
+    return s;
+}
+
+static sph sphere_from_children(sph s0, sph s1) {                 /* bsphere.cpp:248-279 */
+    sph r;
+    v3 v = v3_sub(s1.c, s0.c);
+    float sq = v3_dot(v, v);
+    float dr = s1.r - s0.r;
+    if ((dr * dr) >= sq) {
+        r = (s1.r >= s0.r) ? s1 : s0;
+    } else {
+        float dist = sqrtf(sq);
+        r.r = (dist + s0.r + s1.r) * 0.5f;
+        r.c = s0.c;
+        if (dist > 0.001f) {
+            v = v3_make(v.x / dist, v.y / dist, v.z / dist);
+            r.c = v3_add(r.c, v3_scale(v, r.r - s0.r));
+        }
+    }
+    r.r *= 1.0001f;
+    return r;
+}
+
+/* out_spheres / out_sphere_group: 2 * n_groups - 1 entries. Returns the number of spheres written. */
+uint32_t orc_build_hierarchy(const float *positions, uint32_t n_groups, const uint32_t *group_first, const uint32_t *idx_positions,
+                             rt_bsphere *out_spheres, int32_t *out_sphere_group) {
+    if (n_groups == 0) return 0;
+    uint32_t total = 2 * n_groups - 1;
+    sph *S = (sph *)malloc(sizeof(sph) * total);
+    int32_t *c0 = (int32_t *)malloc(sizeof(int32_t) * total), *c1 = (int32_t *)malloc(sizeof(int32_t) * total);
+    for (uint32_t g = 0; g < n_groups; ++g) {                     /* bsphere.cpp:232-246, 384-393 */
+        uint32_t n = group_first[g + 1] - group_first[g];
+        v3 *pts = (v3 *)calloc(n ? n : 1, sizeof(v3));
+        for (uint32_t i = 0; i < n; ++i) pts[i] = v3_ld(positions + 3 * (size_t)idx_positions[group_first[g] + i]);
+        sph r = eigen_sphere(pts, n);
+        S[g] = ritter_iterative(r, pts, n);
+        free(pts);
+        c0[g] = -1; c1[g] = -1;
+    }
+    uint32_t *list = (uint32_t *)malloc(sizeof(uint32_t) * n_groups), m = n_groups, created = n_groups;
+    for (uint32_t g = 0; g < n_groups; ++g) list[g] = g;
+    while (m >= 2) {                                              /* bsphere.cpp:281-314, 405-427 */
+        float best = FLT_MAX; uint32_t bi = m, bj = m; sph merged = S[list[0]];
+        for (uint32_t i = 0; i < m; ++i)
+            for (uint32_t j = i + 1; j < m; ++j) {
+                sph parent = sphere_from_children(S[list[i]], S[list[j]]);
+                if (parent.r < best) { bi = i; bj = j; merged = parent; best = parent.r; }
+            }
+        uint32_t a = list[bi], b = list[bj];
+        memmove(list + bj, list + bj + 1, sizeof(uint32_t) * (m - bj - 1));      /* erase the later index first */
+        memmove(list + bi, list + bi + 1, sizeof(uint32_t) * (m - 1 - bi - 1));
+        m -= 2;
+        S[created] = merged; c0[created] = (int32_t)a; c1[created] = (int32_t)b;
+        list[m++] = created++;
+    }
+    /* FlattenHierarchyTree (bsphere.cpp:328-350): pre-order, c0 subtree before c1, child index 0 = leaf sentinel */
+    uint32_t *stack = (uint32_t *)malloc(sizeof(uint32_t) * (total + 1)), *slot_of = (uint32_t *)malloc(sizeof(uint32_t) * total), sp = 0, next = 0;
+    stack[sp++] = list[0];
+    uint32_t *order = (uint32_t *)malloc(sizeof(uint32_t) * total);
+    while (sp) {
+        uint32_t n = stack[--sp];
+        slot_of[n] = next; order[next++] = n;
+        if (c0[n] >= 0) { stack[sp++] = (uint32_t)c1[n]; stack[sp++] = (uint32_t)c0[n]; }
+    }
+    for (uint32_t k = 0; k < next; ++k) {
+        uint32_t n = order[k];
+        out_spheres[k].center[0] = S[n].c.x; out_spheres[k].center[1] = S[n].c.y; out_spheres[k].center[2] = S[n].c.z;
+        out_spheres[k].radius = S[n].r;
+        out_spheres[k].c0 = c0[n] >= 0 ? slot_of[c0[n]] : 0;
+        out_spheres[k].c1 = c1[n] >= 0 ? slot_of[c1[n]] : 0;
+        out_sphere_group[k] = c0[n] >= 0 ? -1 : (int32_t)n;
+    }
+    free(S); free(c0); free(c1); free(list); free(stack); free(slot_of); free(order);
+    return next;
+}
+
 /* ---- function-level probes --------------------------------------------------------------- */
 void orc_rng_next_n(uint64_t seed, uint32_t n, uint64_t *out) {
     orc_rng r; orc_rng_seed(&r, seed);

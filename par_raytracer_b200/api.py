@@ -28,7 +28,7 @@ RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
            "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat",
-           "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap"]
+           "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap", "rt_build_group_hierarchy"]
 
 
 class RtError(RuntimeError):
@@ -67,6 +67,18 @@ def rng_kat(seed: int, n: int, device: int = 0) -> np.ndarray:
     out = np.zeros(n, np.uint64)
     _check(load_library().rt_rng_kat(C.c_int(device), C.c_uint64(seed), C.c_uint32(n), _p(out)), "rt_rng_kat")
     return out
+
+
+def build_group_hierarchy(scene: SceneData, device: int = 0):
+    """BuildHierarchy (bsphere.cpp:379-444) on the GPU: returns (spheres, sphere_group) bit-identical to the reference's."""
+    from .types import BSPHERE
+    G = scene.n_groups
+    spheres = np.zeros(max(1, 2 * G - 1), BSPHERE); sg = np.zeros(max(1, 2 * G - 1), np.int32)
+    n = C.c_uint32(0)
+    _check(load_library().rt_build_group_hierarchy(C.c_int(device), _p(scene.positions), C.c_uint32(len(scene.positions)), C.c_uint32(G),
+                                                   _p(scene.group_first), _p(scene.idx_positions), _p(spheres), _p(sg), C.byref(n)),
+           "rt_build_group_hierarchy")
+    return spheres[:n.value], sg[:n.value]
 
 
 def tonemap(frame: np.ndarray, device: int = 0):

@@ -14,6 +14,7 @@
 
 #include "../../include/rt_b200.h"
 #include "rt_build.cuh"
+#include "rt_groups.cuh"
 #include "rt_common.cuh"
 #include "rt_rng.cuh"
 #include "rt_raygen.cuh"
@@ -1142,4 +1143,76 @@ extern "C" int rt_tonemap(int device, const float *rgba_host, uint32_t width, ui
     if (rc == RT_OK && cudaMemcpy(out_rgba8_host, d_out, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(RT_ERR_CUDA, "download failed");
     cudaFree(d_in); cudaFree(d_out);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rt_build_group_hierarchy: BuildHierarchy (bsphere.cpp:379-444) on the GPU, bit-identical output
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_build_group_hierarchy(int device, const float *positions, uint32_t n_positions, uint32_t n_groups, const uint32_t *group_first,
+                                        const uint32_t *idx_positions, rt_bsphere *out_spheres, int32_t *out_sphere_group, uint32_t *out_count) {
+    g_err.clear();
+    if (out_count) *out_count = 0;
+    if (n_groups == 0) return RT_OK;
+    if (!positions || !group_first || !idx_positions || !out_spheres || !out_sphere_group) return fail(RT_ERR_ARG, "null argument");
+    if (n_groups > 65535u) return fail(RT_ERR_ARG, "at most 65535 mesh groups (got %u)", n_groups);
+    const uint64_t n_idx = group_first[n_groups];
+    for (uint32_t g = 0; g < n_groups; ++g) if (group_first[g + 1] <= group_first[g]) return fail(RT_ERR_ARG, "group %u is empty", g);
+    for (uint64_t i = 0; i < n_idx; ++i) if (idx_positions[i] >= n_positions) return fail(RT_ERR_ARG, "vertex index out of range at %llu", (unsigned long long)i);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const uint32_t total = 2 * n_groups - 1;
+    DevArena mem;
+    auto done = [&](int r) { mem.release(); return r; };
+#define CKG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    float *d_pos, *d_pts; uint32_t *d_gf, *d_idx, *d_list[2]; GSphere *d_S; int32_t *d_c0, *d_c1; unsigned long long *d_best;
+    CKG(mem.alloc(&d_pos, 3 * (size_t)n_positions)); CKG(mem.alloc(&d_pts, 3 * (size_t)n_idx)); CKG(mem.alloc(&d_gf, (size_t)n_groups + 1));
+    CKG(mem.alloc(&d_idx, (size_t)n_idx)); CKG(mem.alloc(&d_list[0], n_groups)); CKG(mem.alloc(&d_list[1], n_groups));
+    CKG(mem.alloc(&d_S, total)); CKG(mem.alloc(&d_c0, total)); CKG(mem.alloc(&d_c1, total)); CKG(mem.alloc(&d_best, 1));
+    CKG(cudaMemcpy(d_pos, positions, 12 * (size_t)n_positions, cudaMemcpyHostToDevice));
+    CKG(cudaMemcpy(d_gf, group_first, 4 * ((size_t)n_groups + 1), cudaMemcpyHostToDevice));
+    CKG(cudaMemcpy(d_idx, idx_positions, 4 * (size_t)n_idx, cudaMemcpyHostToDevice));
+    CKG(cudaMemset(d_c0, 0xFF, 4 * (size_t)total)); CKG(cudaMemset(d_c1, 0xFF, 4 * (size_t)total));
+    CKG(cudaMemset(d_best, 0xFF, 8));
+    {
+        std::vector<uint32_t> iota(n_groups);
+        for (uint32_t g = 0; g < n_groups; ++g) iota[g] = g;
+        CKG(cudaMemcpy(d_list[0], iota.data(), 4 * (size_t)n_groups, cudaMemcpyHostToDevice));
+    }
+    k_group_leaf_spheres<<<cdiv(n_groups, 32), 32>>>(d_pos, d_gf, d_idx, n_groups, d_pts, d_S);
+    int cur = 0;
+    uint32_t created = n_groups;
+    for (uint32_t m = n_groups; m >= 2; --m) {          // every merge removes two spheres and appends one
+        k_group_pair_min<<<m, 256>>>(m, d_list[cur], d_S, d_best);
+        k_group_apply_merge<<<1, 1024>>>(m, d_list[cur], d_list[cur ^ 1], d_S, d_c0, d_c1, created, d_best);
+        created++;
+        cur ^= 1;
+    }
+    { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "group hierarchy launch failed: %s", cudaGetErrorString(e_))); }
+    std::vector<GSphere> S(total); std::vector<int32_t> c0(total), c1(total);
+    uint32_t root = 0;
+    CKG(cudaMemcpy(S.data(), d_S, sizeof(GSphere) * (size_t)total, cudaMemcpyDeviceToHost));
+    CKG(cudaMemcpy(c0.data(), d_c0, 4 * (size_t)total, cudaMemcpyDeviceToHost));
+    CKG(cudaMemcpy(c1.data(), d_c1, 4 * (size_t)total, cudaMemcpyDeviceToHost));
+    CKG(cudaMemcpy(&root, d_list[cur], 4, cudaMemcpyDeviceToHost));
+    // FlattenHierarchyTree (bsphere.cpp:328-350): pre-order, child index 0 == leaf sentinel -- pure index bookkeeping, done on the host
+    std::vector<uint32_t> stack, order, slot_of(total, 0);
+    stack.push_back(root);
+    while (!stack.empty()) {
+        uint32_t n = stack.back(); stack.pop_back();
+        if (n >= total) return done(fail(RT_ERR_STATE, "group hierarchy corrupt"));
+        slot_of[n] = (uint32_t)order.size(); order.push_back(n);
+        if (c0[n] >= 0) { stack.push_back((uint32_t)c1[n]); stack.push_back((uint32_t)c0[n]); }
+        if (order.size() > total) return done(fail(RT_ERR_STATE, "group hierarchy corrupt"));
+    }
+    for (size_t k = 0; k < order.size(); ++k) {
+        uint32_t n = order[k];
+        out_spheres[k].center[0] = S[n].x; out_spheres[k].center[1] = S[n].y; out_spheres[k].center[2] = S[n].z; out_spheres[k].radius = S[n].r;
+        out_spheres[k].c0 = c0[n] >= 0 ? slot_of[c0[n]] : 0;
+        out_spheres[k].c1 = c1[n] >= 0 ? slot_of[c1[n]] : 0;
+        out_sphere_group[k] = c0[n] >= 0 ? -1 : (int32_t)n;
+    }
+    if (out_count) *out_count = (uint32_t)order.size();
+    return done(RT_OK);
+#undef CKG
 }

@@ -257,3 +257,30 @@ def test_tonemap_on_device(gscene):
     api.tonemap_device(f.data_ptr(), gs.W, gs.H, out8.data_ptr(), stream=st)
     d2 = np.abs(out8.cpu().numpy().reshape(gs.H, gs.W, 4).astype(np.int32) - gs.tonemap_rgba8.astype(np.int32))
     assert d2.max() <= 1 and (d2 != 0).mean() <= 0.01
+
+
+def test_group_hierarchy_build_is_the_references(golden_scene):
+    """rt_build_group_hierarchy == the reference's BuildHierarchy output (golden: exported from the compiled reference), bit for bit."""
+    gs = golden_scene
+    sp, sg = api.build_group_hierarchy(gs.scene)
+    assert sp.tobytes() == gs.scene.spheres.tobytes()
+    assert np.array_equal(sg, gs.scene.sphere_group)
+
+
+def test_group_hierarchy_build_against_oracle_256_groups():
+    sd = scenes.heightfield_scene(64, 64, block=4, textured=False)
+    sp, sg = api.build_group_hierarchy(sd)
+    so, go = oracle.build_hierarchy(sd)
+    assert len(sp) == 2 * sd.n_groups - 1
+    assert sp.tobytes() == so.tobytes() and np.array_equal(sg, go)
+    # and it is a drop-in input: a scene using it renders exactly like the oracle on the same scene
+    import dataclasses
+    sd2 = dataclasses.replace(sd, spheres=sp, sphere_group=sg)
+    S = api.Scene(sd2); O = oracle.OracleScene(sd2)
+    h = sd.camera_hint
+    cam = types.make_camera(h["fov"], 64, 48, h["position"], h["facing"])
+    p = types.default_params(spp=2)
+    rg, hg = S.trace_primary(cam, p, 64, 48, sample_count=2)
+    ro, ho = O.trace_primary(cam, p, 64, 48, None, 0, 64 * 48, 0, 2)
+    assert_hits_equal(hg, ho, "gpu-built group hierarchy")
+    S.close()
