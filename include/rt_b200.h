@@ -264,6 +264,18 @@ int rt_trace_color(rt_scene *scene, const rt_params *params, const rt_ray *rays,
 int rt_build_group_hierarchy(int device, const float *positions, uint32_t n_positions, uint32_t n_groups, const uint32_t *group_first,
                              const uint32_t *idx_positions, rt_bsphere *out_spheres, int32_t *out_sphere_group, uint32_t *out_count);
 
+/* ---- load-time preprocessing (mesh.h:59-129, texture.cpp:85-144) ------------------- */
+
+/* CalculateTangents: per-triangle UV-delta tangents of the bump-mapped groups accumulated on the NORMAL index in triangle
+ * order, then normalised -- bit-identical to the reference (the accumulation order is reproduced). out_tangents: 3 floats per
+ * normal (what rt_scene_desc.tangents expects). group_has_bump[g] != 0 iff the group's material has a bump texture. */
+int rt_calculate_tangents(int device, const float *positions, uint32_t n_positions, const float *texcoords, uint32_t n_texcoords,
+                          uint32_t n_normals, uint32_t n_groups, const uint32_t *group_first, const uint32_t *idx_positions,
+                          const uint32_t *idx_texcoords, const uint32_t *idx_normals, const uint8_t *group_has_bump, float *out_tangents);
+/* ConvertHeightMapToNormalMap + WriteNormal: 1-channel height map -> 3-channel normal map (stored sRGB-encoded like the
+ * reference does). The encode's powf is CUDA's double pow rounded to float: a texel on a truncation boundary may differ by 1. */
+int rt_height_to_normal_map(int device, uint32_t size_x, uint32_t size_y, const uint8_t *height_host, uint8_t *out_rgb_host);
+
 /* ---- WriteFramebufferImage minus the PNG (main.cpp:78-127, color.h:94-111) -------- */
 
 /* Global log-average-luma Reinhard tone map (key 0.18) + Color_Pack to RGBA8 of a W*H float4 frame that is already on the

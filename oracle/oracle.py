@@ -198,3 +198,25 @@ def build_hierarchy(scene: SceneData):
     lib().orc_build_hierarchy.restype = C.c_uint32
     n = lib().orc_build_hierarchy(_p(scene.positions), C.c_uint32(G), _p(scene.group_first), _p(scene.idx_positions), _p(spheres), _p(sg))
     return spheres[:n], sg[:n]
+
+
+def group_has_bump(scene: SceneData) -> np.ndarray:
+    """mesh.h:70: a group takes part in CalculateTangents iff it has a material with a bump texture."""
+    gm = scene.group_material
+    return np.array([1 if (m >= 0 and scene.materials[m]["bump_texture"] >= 0) else 0 for m in gm], np.uint8)
+
+
+def calculate_tangents(scene: SceneData) -> np.ndarray:
+    out = np.zeros((len(scene.normals), 3), np.float32)
+    hb = group_has_bump(scene)
+    lib().orc_calculate_tangents(_p(scene.positions), _p(scene.texcoords), C.c_uint32(len(scene.normals)), C.c_uint32(scene.n_groups),
+                                 _p(scene.group_first), _p(scene.idx_positions), _p(scene.idx_texcoords), _p(scene.idx_normals), _p(hb), _p(out))
+    return out
+
+
+def height_to_normal_map(height: np.ndarray) -> np.ndarray:
+    height = np.ascontiguousarray(height, np.uint8)
+    h, w = height.shape
+    out = np.zeros((h, w, 3), np.uint8)
+    lib().orc_height_to_normal_map(C.c_uint32(w), C.c_uint32(h), _p(height), _p(out))
+    return out

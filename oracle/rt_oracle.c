@@ -950,6 +950,61 @@ uint32_t orc_build_hierarchy(const float *positions, uint32_t n_groups, const ui
     return next;
 }
 
+/* ======================================================================================== */
+/* mesh.h:59-129 CalculateTangents; texture.cpp:85-144 WriteNormal / ConvertHeightMapToNormalMap */
+/* ======================================================================================== */
+void orc_calculate_tangents(const float *positions, const float *texcoords, uint32_t n_normals, uint32_t n_groups, const uint32_t *group_first,
+                            const uint32_t *idx_p, const uint32_t *idx_t, const uint32_t *idx_n, const uint8_t *group_has_bump, float *tangents) {
+    memset(tangents, 0, sizeof(float) * 3 * (size_t)n_normals);
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        if (!group_has_bump[g]) continue;                                      /* mesh.h:70-74 */
+        for (uint32_t i = group_first[g]; i < group_first[g + 1]; i += 3) {
+            v3 p0 = v3_ld(positions + 3 * (size_t)idx_p[i]), p1 = v3_ld(positions + 3 * (size_t)idx_p[i + 1]), p2 = v3_ld(positions + 3 * (size_t)idx_p[i + 2]);
+            const float *uv0 = texcoords + 2 * (size_t)idx_t[i], *uv1 = texcoords + 2 * (size_t)idx_t[i + 1], *uv2 = texcoords + 2 * (size_t)idx_t[i + 2];
+            v3 dp0 = v3_sub(p1, p0), dp1 = v3_sub(p2, p0);
+            float d0x = uv1[0] - uv0[0], d0y = uv1[1] - uv0[1], d1x = uv2[0] - uv0[0], d1y = uv2[1] - uv0[1];
+            float f = (d0x * d1y - d1x * d0y);
+            if (f <= 1e-7) continue;                                           /* float compared with a double literal */
+            f = 1.0f / f;
+            v3 t;
+            t.x = f * (d1y * dp0.x - d0y * dp1.x);
+            t.y = f * (d1y * dp0.y - d0y * dp1.y);
+            t.z = f * (d1y * dp0.z - d0y * dp1.z);
+            for (int k = 0; k < 3; ++k) {
+                float *dst = tangents + 3 * (size_t)idx_n[i + k];
+                dst[0] += t.x; dst[1] += t.y; dst[2] += t.z;
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n_normals; ++i) {
+        v3 t = v3_normalize(v3_ld(tangents + 3 * (size_t)i));
+        tangents[3 * (size_t)i] = t.x; tangents[3 * (size_t)i + 1] = t.y; tangents[3 * (size_t)i + 2] = t.z;
+    }
+}
+
+static inline float linear_to_srgb(float linear) {                             /* color.h:3-11 */
+    if (linear <= 0.0031308f) return 12.92f * linear;
+    return 1.055f * powf(linear, 1.0f / 2.4f) - 0.055f;
+}
+
+void orc_height_to_normal_map(uint32_t sx, uint32_t sy, const uint8_t *height, uint8_t *out_rgb) {   /* texture.cpp:102-125, 85-100 */
+    const float one_over_255 = 1.0f / 255.0f;
+    for (uint32_t y = 0; y < sy; ++y)
+        for (uint32_t x = 0; x < sx; ++x) {
+            uint32_t x1 = (x + 1) % sx, y1 = (y + 1) % sy;
+            float h00 = srgb_to_linear((float)height[y * sx + x] * one_over_255);
+            float h10 = srgb_to_linear((float)height[y * sx + x1] * one_over_255);
+            float h01 = srgb_to_linear((float)height[y1 * sx + x] * one_over_255);
+            float a = 2.5f;
+            v3 n = v3_normalize(v3_make((h01 - h00) * a, (h10 - h00) * a, 1.0f));
+            n = v3_scale(v3_add(n, v3_make(1.0f, 1.0f, 1.0f)), 0.5f);
+            uint8_t *o = out_rgb + 3 * ((size_t)y * sx + x);
+            o[0] = (uint8_t)(linear_to_srgb(n.x) * 255.0f);
+            o[1] = (uint8_t)(linear_to_srgb(n.y) * 255.0f);
+            o[2] = (uint8_t)(linear_to_srgb(n.z) * 255.0f);
+        }
+}
+
 /* ---- function-level probes --------------------------------------------------------------- */
 void orc_rng_next_n(uint64_t seed, uint32_t n, uint64_t *out) {
     orc_rng r; orc_rng_seed(&r, seed);

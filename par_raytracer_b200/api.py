@@ -28,7 +28,8 @@ RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
            "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat",
-           "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap", "rt_build_group_hierarchy"]
+           "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap", "rt_build_group_hierarchy",
+           "rt_calculate_tangents", "rt_height_to_normal_map"]
 
 
 class RtError(RuntimeError):
@@ -79,6 +80,26 @@ def build_group_hierarchy(scene: SceneData, device: int = 0):
                                                    _p(scene.group_first), _p(scene.idx_positions), _p(spheres), _p(sg), C.byref(n)),
            "rt_build_group_hierarchy")
     return spheres[:n.value], sg[:n.value]
+
+
+def calculate_tangents(scene: SceneData, device: int = 0) -> np.ndarray:
+    """CalculateTangents (mesh.h:59-129) on the GPU, bit-identical to the reference: (n_normals, 3) float32."""
+    hb = np.array([1 if (m >= 0 and scene.materials[m]["bump_texture"] >= 0) else 0 for m in scene.group_material], np.uint8)
+    out = np.zeros((len(scene.normals), 3), np.float32)
+    _check(load_library().rt_calculate_tangents(C.c_int(device), _p(scene.positions), C.c_uint32(len(scene.positions)), _p(scene.texcoords),
+                                                C.c_uint32(len(scene.texcoords)), C.c_uint32(len(scene.normals)), C.c_uint32(scene.n_groups),
+                                                _p(scene.group_first), _p(scene.idx_positions), _p(scene.idx_texcoords), _p(scene.idx_normals),
+                                                _p(hb), _p(out)), "rt_calculate_tangents")
+    return out
+
+
+def height_to_normal_map(height: np.ndarray, device: int = 0) -> np.ndarray:
+    """ConvertHeightMapToNormalMap (texture.cpp:102-144) on the GPU: (H, W) uint8 -> (H, W, 3) uint8."""
+    height = np.ascontiguousarray(height, np.uint8)
+    h, w = height.shape
+    out = np.zeros((h, w, 3), np.uint8)
+    _check(load_library().rt_height_to_normal_map(C.c_int(device), C.c_uint32(w), C.c_uint32(h), _p(height), _p(out)), "rt_height_to_normal_map")
+    return out
 
 
 def tonemap(frame: np.ndarray, device: int = 0):

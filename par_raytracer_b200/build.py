@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rt_api.cu")
 OUT = os.path.join(HERE, "librt_b200.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("rt_api.cu", "rt_build.cuh", "rt_common.cuh", "rt_rng.cuh", "rt_raygen.cuh", "rt_groups.cuh", "rt_shade.cuh", "rt_trace.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("rt_api.cu", "rt_build.cuh", "rt_common.cuh", "rt_rng.cuh", "rt_raygen.cuh", "rt_groups.cuh", "rt_preprocess.cuh", "rt_shade.cuh", "rt_trace.cuh")]
 DEPS.append(os.path.join(HERE, "..", "include", "rt_b200.h"))
 
 NVCC_FLAGS = [

@@ -15,6 +15,7 @@
 #include "../../include/rt_b200.h"
 #include "rt_build.cuh"
 #include "rt_groups.cuh"
+#include "rt_preprocess.cuh"
 #include "rt_common.cuh"
 #include "rt_rng.cuh"
 #include "rt_raygen.cuh"
@@ -1215,4 +1216,82 @@ extern "C" int rt_build_group_hierarchy(int device, const float *positions, uint
     if (out_count) *out_count = (uint32_t)order.size();
     return done(RT_OK);
 #undef CKG
+}
+
+// ---------------------------------------------------------------------------------------------
+// rt_calculate_tangents / rt_height_to_normal_map: the reference's load-time preprocessing (mesh.h:59-129, texture.cpp:85-144)
+// ---------------------------------------------------------------------------------------------
+extern "C" int rt_calculate_tangents(int device, const float *positions, uint32_t n_positions, const float *texcoords, uint32_t n_texcoords,
+                                     uint32_t n_normals, uint32_t n_groups, const uint32_t *group_first, const uint32_t *idx_positions,
+                                     const uint32_t *idx_texcoords, const uint32_t *idx_normals, const uint8_t *group_has_bump, float *out_tangents) {
+    g_err.clear();
+    if (!out_tangents) return fail(RT_ERR_ARG, "null argument");
+    memset(out_tangents, 0, sizeof(float) * 3 * (size_t)n_normals);
+    if (n_groups == 0 || n_normals == 0) return RT_OK;
+    if (!positions || !texcoords || !group_first || !idx_positions || !idx_texcoords || !idx_normals || !group_has_bump) return fail(RT_ERR_ARG, "null argument");
+    const uint64_t n_idx = group_first[n_groups];
+    if (n_idx % 3 || n_idx / 3 > 200000000ull) return fail(RT_ERR_ARG, "bad index count");
+    for (uint64_t i = 0; i < n_idx; ++i)
+        if (idx_positions[i] >= n_positions || idx_texcoords[i] >= n_texcoords || idx_normals[i] >= n_normals) return fail(RT_ERR_ARG, "vertex index out of range at %llu", (unsigned long long)i);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const uint32_t n_tris = (uint32_t)(n_idx / 3);
+    uint32_t n_pad = BITONIC_TILE;
+    while (n_pad < n_idx) n_pad <<= 1;
+    DevArena mem;
+    auto done = [&](int r) { mem.release(); return r; };
+#define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); } while (0)
+    float *d_pos, *d_tc, *d_tan; uint32_t *d_ip, *d_it, *d_in, *d_gf, *vals; uint8_t *d_hb; float4 *tri_tan; uint64_t *keys;
+    CKT(mem.alloc(&d_pos, 3 * (size_t)n_positions)); CKT(mem.alloc(&d_tc, 2 * (size_t)n_texcoords)); CKT(mem.alloc(&d_tan, 3 * (size_t)n_normals));
+    CKT(mem.alloc(&d_ip, (size_t)n_idx)); CKT(mem.alloc(&d_it, (size_t)n_idx)); CKT(mem.alloc(&d_in, (size_t)n_idx)); CKT(mem.alloc(&d_gf, (size_t)n_groups + 1));
+    CKT(mem.alloc(&d_hb, n_groups)); CKT(mem.alloc(&tri_tan, n_tris)); CKT(mem.alloc(&keys, n_pad)); CKT(mem.alloc(&vals, n_pad));
+    CKT(cudaMemcpy(d_pos, positions, 12 * (size_t)n_positions, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_tc, texcoords, 8 * (size_t)n_texcoords, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_ip, idx_positions, 4 * (size_t)n_idx, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_it, idx_texcoords, 4 * (size_t)n_idx, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_in, idx_normals, 4 * (size_t)n_idx, cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_gf, group_first, 4 * ((size_t)n_groups + 1), cudaMemcpyHostToDevice));
+    CKT(cudaMemcpy(d_hb, group_has_bump, n_groups, cudaMemcpyHostToDevice));
+    CKT(cudaMemset(d_tan, 0, 12 * (size_t)n_normals));
+    TangentInput in; in.positions = d_pos; in.texcoords = d_tc; in.idx_p = d_ip; in.idx_t = d_it; in.idx_n = d_in; in.group_first = d_gf;
+    in.group_has_bump = d_hb; in.n_groups = n_groups; in.n_tris = n_tris;
+    k_tri_tangents<<<cdiv((n_pad + 2) / 3 + 1, 256), 256>>>(in, tri_tan, keys, vals, n_pad);
+    k_bitonic_shared<<<n_pad / BITONIC_TILE, 1024>>>(keys, vals, 2, BITONIC_TILE, 0);
+    for (uint64_t k = 2ull * BITONIC_TILE; k <= n_pad; k <<= 1) {
+        for (uint32_t j = (uint32_t)(k >> 1); j >= BITONIC_TILE; j >>= 1) k_bitonic_global<<<cdiv(n_pad, 256), 256>>>(keys, vals, n_pad, j, (uint32_t)k);
+        k_bitonic_shared<<<n_pad / BITONIC_TILE, 1024>>>(keys, vals, (uint32_t)k, (uint32_t)k, 1);
+    }
+    k_sum_tangents<<<cdiv(n_pad, 256), 256>>>(keys, vals, n_pad, tri_tan, d_tan);
+    { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "tangent launch failed: %s", cudaGetErrorString(e_))); }
+    CKT(cudaMemcpy(out_tangents, d_tan, 12 * (size_t)n_normals, cudaMemcpyDeviceToHost));
+    return done(RT_OK);
+#undef CKT
+}
+
+extern "C" int rt_height_to_normal_map(int device, uint32_t size_x, uint32_t size_y, const uint8_t *height_host, uint8_t *out_rgb_host) {
+    g_err.clear();
+    if (!height_host || !out_rgb_host || !size_x || !size_y) return fail(RT_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(RT_ERR_CUDA, "no CUDA device: librt_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const size_t n = (size_t)size_x * size_y;
+    float lut[256]; host_srgb_lut(lut);
+    uint8_t *d_h = nullptr, *d_o = nullptr; float *d_lut = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_h, n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_o, 3 * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_lut, sizeof(lut));
+    if (e == cudaSuccess) e = cudaMemcpy(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_h, height_host, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        dim3 grid(cdiv(size_x, 128), size_y);
+        k_height_to_normal<<<grid, 128>>>(size_x, size_y, d_h, d_lut, d_o);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_rgb_host, d_o, 3 * n, cudaMemcpyDeviceToHost);
+    if (d_h) cudaFree(d_h);
+    if (d_o) cudaFree(d_o);
+    if (d_lut) cudaFree(d_lut);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, "height map conversion failed: %s", cudaGetErrorString(e));
+    return RT_OK;
 }

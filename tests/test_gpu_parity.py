@@ -284,3 +284,16 @@ def test_group_hierarchy_build_against_oracle_256_groups():
     ro, ho = O.trace_primary(cam, p, 64, 48, None, 0, 64 * 48, 0, 2)
     assert_hits_equal(hg, ho, "gpu-built group hierarchy")
     S.close()
+
+
+def test_load_time_preprocessing_on_device(golden_scene, golden_functions):
+    """CalculateTangents on the GPU == the tangents the reference computed (bit for bit: accumulation order reproduced);
+    ConvertHeightMapToNormalMap: at most a handful of texels one code value off (powf)."""
+    gs = golden_scene
+    t = api.calculate_tangents(gs.scene)
+    assert np.array_equal(bits(t), bits(gs.scene.tangents))
+    nm = api.height_to_normal_map(golden_functions["height_map"])
+    d = np.abs(nm.astype(np.int32) - golden_functions["normal_map"].astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+    big = scenes.heightfield_scene(96, 96, block=8, textured=True, tex_size=64)
+    assert np.array_equal(bits(api.calculate_tangents(big)), bits(oracle.calculate_tangents(big)))
