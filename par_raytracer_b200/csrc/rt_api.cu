@@ -114,6 +114,7 @@ struct rt_scene {
     size_t tev_used = 0;
     std::vector<std::pair<uint64_t, uint64_t>> wave_log;   // (closest, shadow) rays per issued wave, aligned with tev (RT_B200_WAVE_LOG=1)
     int sm_count = 148;
+    bool box_bounds = true;              // child bound of the traversal: axis-aligned boxes (default) or sphere + slab (RT_B200_BOUNDS=sphere)
     int trace_grid = 148 * 8;            // persistent grid of k_trace_wave: resident blocks of the whole chip
     int logic_grid = 148 * 6;            // same for k_logic
 };
@@ -226,7 +227,8 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     uint32_t kept_nodes = 0, depth = 0, iterations = 0;
     int32_t root_temp = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        const int pair_mode = attempt;       // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n)
+        // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n); mode 2 = surface-area search cost (experiment knob)
+        const int pair_mode = attempt ? 1 : (getenv("RT_B200_PLOC_AREA") ? 2 : 0);
         k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, tri_lo, tri_hi, tri_nrm0, tri_slab, cn[0], t); CKLB("k_ploc_init");
         uint32_t m = n, created = 0;
         int cur = 0;
@@ -261,14 +263,14 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         if (attempt == 1) return done(fail(RT_ERR_STATE, "hierarchy depth %u exceeds traversal stack", depth));
     }
 
-    HNode *nodes;
-    CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
+    HNode *nodes; BNode *bnodes;
+    CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes))); CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes)));
     if (n > 1) {
         k_slot_to_tri<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_offset, slot_tri); CKLB("k_slot_to_tri");
         k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit");
     }
     if (kept_nodes > 0) {
-        k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes); CKLB("k_emit_nodes");
+        k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes, bnodes); CKLB("k_emit_nodes");
         sc->d.root = 0;
     } else {
         sc->d.root = -(int)(1u + 0u * 8u + n);     // the whole scene is one cluster (n <= RT_LEAF_MAX)
@@ -281,7 +283,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     CKB(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 
-    sc->d.nodes = nodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
+    sc->d.nodes = nodes; sc->d.bnodes = bnodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
     sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object;
     sc->d.n_tris = n; sc->d.n_nodes = kept_nodes;
     {   // every sphere lies inside the root sphere: |c|_1 + r <= |c_root|_1 + sqrt(3) * 2 r_root + r_root
@@ -290,7 +292,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         sc->d.cull_bound = fabsf(rs.x) + fabsf(rs.y) + fabsf(rs.z) + 4.5f * rs.w;
     }
     sc->info[0] = n; sc->info[1] = 0; sc->info[2] = kept_nodes; sc->info[3] = depth;
-    sc->info[4] = (uint64_t)kept_nodes * sizeof(HNode); sc->info[5] = (uint64_t)n * sizeof(TriRec);
+    sc->info[4] = (uint64_t)kept_nodes * (sc->box_bounds ? sizeof(BNode) : sizeof(HNode)); sc->info[5] = (uint64_t)n * sizeof(TriRec);
     sc->info[6] = (uint64_t)(ms * 1000.0f); sc->info[7] = iterations;
     return done(RT_OK);
 #undef CKB
@@ -361,7 +363,10 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     CKS(cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, device));
     {
         int per_sm = 0;
-        CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false>, RT_TRACE_BLOCK, 0));
+        const char *be = getenv("RT_B200_BOUNDS");      // "sphere": the sphere + slab child bound (kept for the comparison in profiles/)
+        sc->box_bounds = !(be && strcmp(be, "sphere") == 0);
+        if (sc->box_bounds) CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, true>, RT_TRACE_BLOCK, 0));
+        else CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, false>, RT_TRACE_BLOCK, 0));
         sc->trace_grid = sc->sm_count * std::max(1, per_sm);
         CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logic, 128, 0));
         sc->logic_grid = sc->sm_count * std::max(1, per_sm) * 2;
@@ -607,9 +612,10 @@ static uint32_t env_knob(const char *name, uint32_t dflt) {
     return (v < 1 || v > 32) ? dflt : v;
 }
 static void set_fetch_knobs(WaveQueues &w) {
-    static uint32_t a = 0, b = 0, c = 0;
-    if (!a) { a = env_knob("RT_B200_FETCH_MIN", RT_FETCH_MIN); b = env_knob("RT_B200_FETCH_PRIMARY", RT_FETCH_MIN); c = env_knob("RT_B200_FETCH_SHADOW", RT_FETCH_MIN); }
-    w.fetch_min = a; w.fetch_min_primary = b; w.fetch_min_shadow = c;
+    uint32_t a = 0, b = 0, c = 0, d = 0;      // read per launch (microseconds): lets one process sweep the knobs
+    { a = env_knob("RT_B200_FETCH_MIN", RT_FETCH_MIN); b = env_knob("RT_B200_FETCH_PRIMARY", RT_FETCH_MIN); c = env_knob("RT_B200_FETCH_SHADOW", RT_FETCH_MIN);
+              d = env_knob("RT_B200_LEAF_WAIT", RT_LEAF_WAIT); }
+    w.fetch_min = a; w.fetch_min_primary = b; w.fetch_min_shadow = c; w.leaf_wait = d;
 }
 
 static WaveQueues wave_queues(rt_scene *sc, int cur, uint32_t n_closest_max) {
@@ -628,8 +634,13 @@ static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, cons
     cudaStream_t st = sc->stream;
     CK(cudaMemsetAsync(w.next, 0, 4, st));
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sc->trace_grid, std::max<uint64_t>(1, (work_bound + RT_TRACE_BLOCK - 1) / RT_TRACE_BLOCK));
-    if (count) k_trace_wave<true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
-    else k_trace_wave<false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
+    if (sc->box_bounds) {
+        if (count) k_trace_wave<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
+        else k_trace_wave<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
+    } else {
+        if (count) k_trace_wave<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
+        else k_trace_wave<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
+    }
     CKL("k_trace_wave");
     return RT_OK;
 }

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(256) k_ploc_nn(uint32_t m, const int32_t *cl_n
     __syncthreads();
     uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= m) return;
-    if (pair_mode) { uint32_t j = i ^ 1u; nn[i] = j < m ? j : i; return; }
+    if (pair_mode == 1) { uint32_t j = i ^ 1u; nn[i] = j < m ? j : i; return; }
     float4 lo = slo[threadIdx.x + PLOC_RADIUS], hi = shi[threadIdx.x + PLOC_RADIUS];
     float best = FLT_MAX; uint32_t bj = i;
     for (int o = -PLOC_RADIUS; o <= PLOC_RADIUS; ++o) {
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) k_ploc_nn(uint32_t m, const int32_t *cl_n
         float4 l2 = slo[threadIdx.x + PLOC_RADIUS + o], h2 = shi[threadIdx.x + PLOC_RADIUS + o];
         if (l2.w < 0.0f) continue;
         float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
-        float c = dx * dx + dy * dy + dz * dz;
+        float c = pair_mode == 2 ? dx * dy + dy * dz + dz * dx : dx * dx + dy * dy + dz * dz;     // 2: half surface area of the merged box
         if (c < best) { best = c; bj = (uint32_t)((int)i + o); }
     }
     nn[i] = bj;
@@ -415,12 +415,21 @@ __global__ void __launch_bounds__(256) k_refit(uint32_t n, uint32_t n_total, Tem
 }
 
 __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, const uint32_t *tri_offset, const uint32_t *kept_index,
-                             HNode *nodes) {
+                             HNode *nodes, BNode *bnodes) {
     uint32_t v = n + blockIdx.x * blockDim.x + threadIdx.x;   // internal temp nodes only
     if (v >= n_nodes_total) return;
     if (t.size[v] <= RT_LEAF_MAX) return;
     HNode o;
     int32_t a = t.c0[v], b = t.c1[v];
+    {
+        float4 la = t.lo[a], ha = t.hi[a], lb = t.lo[b], hb = t.hi[b];      // exact vertex extents; the traversal pads them per ray
+        BNode q;
+        q.a = make_float4(la.x, la.y, la.z, ha.x); q.b = make_float4(ha.y, ha.z, lb.x, lb.y); q.c = make_float4(lb.z, hb.x, hb.y, hb.z);
+        q.c0 = t.size[a] > RT_LEAF_MAX ? (int32_t)kept_index[a] : leaf_ref(tri_offset[a], t.size[a]);
+        q.c1 = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
+        q.pad0 = q.pad1 = 0;
+        bnodes[kept_index[v]] = q;
+    }
     o.s0 = t.sphere[a]; o.s1 = t.sphere[b];
     o.p0 = t.slab[a]; o.p1 = t.slab[b];
     o.dmax0 = t.nsum[a].w; o.dmax1 = t.nsum[b].w;

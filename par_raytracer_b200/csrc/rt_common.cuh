@@ -60,6 +60,16 @@ struct __align__(16) HNode {
 };
 static_assert(sizeof(HNode) == 80, "HNode");
 
+// Box form of the same node (the default traversal bound, see rt_trace.cuh): both children's axis-aligned bounds in the
+// parent, 64 bytes = half a cache line, four 16-byte loads. Same tree, same child refs as HNode.
+//   a = (lo0.x lo0.y lo0.z hi0.x)  b = (hi0.y hi0.z lo1.x lo1.y)  c = (lo1.z hi1.x hi1.y hi1.z)
+struct __align__(16) BNode {
+    float4 a, b, c;
+    int32_t c0, c1;
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(BNode) == 64, "BNode");
+
 RT_DEVICE int leaf_ref(uint32_t first, uint32_t count) { return -(int)(1u + first * 8u + count); }
 RT_DEVICE uint32_t leaf_first(int ref) { return ((uint32_t)(-ref) - 1u) >> 3; }
 RT_DEVICE uint32_t leaf_count(int ref) { return ((uint32_t)(-ref) - 1u) & 7u; }
@@ -92,7 +102,8 @@ struct DevLight {             // scene.h:9-15
 };
 
 struct DevScene {
-    const HNode *nodes;
+    const HNode *nodes;            // sphere + slab child bounds (RT_B200_BOUNDS=sphere)
+    const BNode *bnodes;           // axis-aligned child bounds (default)
     const TriRec *tris;
     const uint32_t *tri_rank;      // tie-break rank: position in the reference's leaf visit order
     const float4 *tri_uv;          // 2 per triangle: (u0 v0 u1 v1) (u2 v2 material_bits -)

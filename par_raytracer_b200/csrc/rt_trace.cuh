@@ -94,6 +94,32 @@ RT_DEVICE bool tri_test(const TriRec &r, const RayCtx &c, float &t_out, float &v
     return true;
 }
 
+// ---- axis-aligned child bounds (default) ---------------------------------------------------------------------
+// Slab test of a ray against one child box fattened by the per-ray `slack` on every side (same slack, same argument as
+// cull_child). With i = 1/d per axis, the parameter of the fattened lo plane is (lo - slack - o) i = lo i - (o + slack) i and of the
+// fattened hi plane (hi + slack - o) i = hi i - (o - slack) i, whatever the sign of d: one FMA per plane against two per-ray
+// constants per axis, so the padding is free. |d| is clamped away from zero (1e-20: the fake drift over any t is far below
+// the slack) so that no 0 * inf appears. FMA / approximate reciprocal are allowed: the result only prunes.
+struct BoxRay { float ix, iy, iz, clx, cly, clz, chx, chy, chz; };
+
+RT_DEVICE float safe_rcp(float d) { return approx_rcp(fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d); }
+
+RT_DEVICE void box_ray_setup(BoxRay &R, f3 o, f3 d, float slack) {
+    R.ix = safe_rcp(d.x); R.iy = safe_rcp(d.y); R.iz = safe_rcp(d.z);
+    R.clx = -(o.x + slack) * R.ix; R.chx = -(o.x - slack) * R.ix;
+    R.cly = -(o.y + slack) * R.iy; R.chy = -(o.y - slack) * R.iy;
+    R.clz = -(o.z + slack) * R.iz; R.chz = -(o.z - slack) * R.iz;
+}
+
+RT_DEVICE bool box_child(float lx, float ly, float lz, float hx, float hy, float hz, const BoxRay &R, float tmax, float &tn) {
+    float tlx = __fmaf_rn(lx, R.ix, R.clx), thx = __fmaf_rn(hx, R.ix, R.chx);
+    float tly = __fmaf_rn(ly, R.iy, R.cly), thy = __fmaf_rn(hy, R.iy, R.chy);
+    float tlz = __fmaf_rn(lz, R.iz, R.clz), thz = __fmaf_rn(hz, R.iz, R.chz);
+    tn = fmaxf(fmaxf(fminf(tlx, thx), fminf(tly, thy)), fmaxf(fminf(tlz, thz), 0.0f));       // FMNMX3 pairs on sm_100a
+    float tf = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fminf(fmaxf(tlz, thz), tmax));
+    return tn <= tf;
+}
+
 // ---- the wave trace kernel -----------------------------------------------------------------------------
 // One launch traces everything a wave has to trace: the closest-hit rays of the pending recursion nodes AND the
 // shadow rays queued by the previous shading step (ShadeLight, raytracer.cpp:378-411), so a wave pays one
@@ -103,11 +129,19 @@ RT_DEVICE bool tri_test(const TriRec &r, const RayCtx &c, float &t_out, float &v
 // global work counter. A lane whose ray has finished does not wait for the slowest lane of its warp: as soon as
 // RT_FETCH_MIN lanes are idle the warp fetches that many consecutive rays with ONE atomicAdd (consecutive
 // queue entries are spatially coherent: same pixel / neighbouring pixels). Traversal per lane is a short-stack
-// while-while loop: descend internal nodes nearest-child first, then scan the reached cluster.
+// while-while loop: descend internal nodes nearest-child first, then scan the reached cluster. stack[0] holds a
+// sentinel, so "pop" needs no emptiness test: popping the sentinel ends the ray.
+//
+// BOX selects the child bound: axis-aligned boxes (64-byte nodes, ~50 instructions per node visit) or the sphere + slab
+// bound (80-byte nodes, ~105 instructions per visit); both are conservative, so hits are identical (tests run both).
 #define RT_TRACE_BLOCK 128
 #ifndef RT_FETCH_MIN
 #define RT_FETCH_MIN 16
 #endif
+#ifndef RT_LEAF_WAIT
+#define RT_LEAF_WAIT 32
+#endif
+#define RT_DONE ((int)0x80000000)      // never a leaf ref: |leaf ref| <= 1 + 8 * 2e8 + 7 < 2^31
 
 struct WaveQueues {
     RayQueue closest;              // d.w = path slot
@@ -125,9 +159,10 @@ struct WaveQueues {
     uint32_t fetch_min;            // refill the warp once this many lanes are idle (32 = only when all are): bounce rays
     uint32_t fetch_min_primary;    // same while the work counter is still inside the primary rays of wave 0
     uint32_t fetch_min_shadow;     // same inside the shadow-ray region
+    uint32_t leaf_wait;            // leave the node loop once this many live lanes wait at a cluster / have finished (32: only when all do)
 };
 
-template <bool COUNT>
+template <bool COUNT, bool BOX>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float bias, WaveQueues W, PrimaryGen G, TraceCounters *counters) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -139,12 +174,15 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
     bool live = false, exhausted = false;
     uint32_t fetch_min = G.enabled ? W.fetch_min_primary : W.fetch_min;
     RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
+    BoxRay R; R.ix = R.iy = R.iz = R.clx = R.cly = R.clz = R.chx = R.chy = R.chz = 0.0f;
     float inv_dd = 0.0f, dist_sq = -1.0f, slack = 0.0f;
     HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
+    float tcull = FLT_MAX;         // BOX: best.t widened by 1e-5 relative, so a box entered a few ulps beyond best.t is still opened
     uint32_t best_rank = 0xFFFFFFFFu, out_idx = 0, light = 0;
     int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light)
-    int cur = 0, sp = 0;
+    int cur = RT_DONE, sp = 1;
     int stack[RT_STACK_MAX];
+    stack[0] = RT_DONE;
 
     while (true) {
         // ---- warp-cooperative fetch ----
@@ -161,7 +199,10 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                     float4 o4, d4;
                     if (idx < nC) {
                         kind = 0; out_idx = idx;
-                        if (G.enabled) { PathRng pr; f3 po, pd; primary_ray(G, idx, pr, po, pd); o4 = mk4(po, 0.0f); d4 = mk4(pd, 0.0f); }
+                        if (G.enabled) {
+                            PathRng pr; f3 po, pd; primary_ray(G, idx, pr, po, pd); o4 = mk4(po, 0.0f); d4 = mk4(pd, 0.0f);
+                            W.closest.d[idx] = d4;                       // wave 0: the shading step reads the direction back
+                        }
                         else { o4 = W.closest.o[idx]; d4 = W.closest.d[idx]; }
                     }
                     else {
@@ -179,43 +220,66 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                         }
                     }
                     f3 dir = mk3(d4);
-                    c.d = dir;
                     c.o = mk3(o4) + dir * bias;                      // raytracer.cpp:163
                     f3 q = c.o + dir;
                     c.qp = c.o - q;
-                    inv_dd = approx_rcp(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x)));   // culling only
                     slack = RT_CULL_SLACK * (fabsf(c.o.x) + fabsf(c.o.y) + fabsf(c.o.z) + S.cull_bound);
+                    if (BOX) box_ray_setup(R, c.o, dir, slack);
+                    else { c.d = dir; inv_dd = approx_rcp(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x))); }   // culling only
                     best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1; best_rank = 0xFFFFFFFFu;   // raytracer.cpp:166
-                    cur = S.root; sp = 0;
+                    tcull = FLT_MAX;
+                    cur = S.n_tris ? S.root : RT_DONE; sp = 1;
                     live = true;
                 }
             }
         }
         if (__ballot_sync(FULL, live) == 0) break;
 
-        if (live) {
-            bool done = S.n_tris == 0;
-            // ---- descend to the next cluster ----
-            while (!done && cur >= 0) {
-                const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
-                float4 s0 = __ldg(np), s1 = __ldg(np + 1), p0 = __ldg(np + 2), p1 = __ldg(np + 3);
-                float4 m4 = __ldg(np + 4);
-                int2 ch = make_int2(__float_as_int(m4.z), __float_as_int(m4.w));
-                float t0, t1;
-                // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
-                bool h0 = cull_child(s0, p0, m4.x, c.o, c.d, inv_dd, slack, best.t, t0);
-                bool h1 = cull_child(s1, p1, m4.y, c.o, c.d, inv_dd, slack, best.t, t1);
-                if (COUNT) n_sph += 2;
-                bool second_first = h1 & (!h0 | (t1 < t0));
-                int near = second_first ? ch.y : ch.x;
-                int far = second_first ? ch.x : ch.y;
-                if (h0 & h1) stack[sp++] = far;                      // depth <= RT_STACK_MAX - 2 is guaranteed by the build
-                if (h0 | h1) cur = near;
-                else if (sp == 0) done = true;
-                else cur = stack[--sp];
+        // ---- descend to the next cluster ----
+        // The node loop is warp-uniform: it runs while enough lanes still have an internal node to open. A lane that has reached a
+        // cluster (or finished) waits, but only until `leaf_wait` lanes are waiting -- then the warp leaves the loop, scans the
+        // reached clusters, refills finished lanes and comes back. Without the cap the slowest descent of the warp holds every
+        // other lane (ncu: 10 of 32 lanes active in the node loop); idle lanes hold cur = RT_DONE.
+        {
+            const int keep = max(1, __popc(__ballot_sync(FULL, live)) - (int)W.leaf_wait);
+            uint32_t nm = __ballot_sync(FULL, cur >= 0);
+            while (nm != 0) {
+                if (cur >= 0) {
+                    int2 ch; bool h0, h1; float t0, t1;
+                    if (BOX) {
+                        const float4 *np = reinterpret_cast<const float4 *>(S.bnodes + cur);
+                        float4 A = __ldg(np), B = __ldg(np + 1), C = __ldg(np + 2);
+                        ch = __ldg(reinterpret_cast<const int2 *>(np + 3));
+                        h0 = box_child(A.x, A.y, A.z, A.w, B.x, B.y, R, tcull, t0);
+                        h1 = box_child(B.z, B.w, C.x, C.y, C.z, C.w, R, tcull, t1);
+                    } else {
+                        const float4 *np = reinterpret_cast<const float4 *>(S.nodes + cur);
+                        float4 s0 = __ldg(np), s1 = __ldg(np + 1), p0 = __ldg(np + 2), p1 = __ldg(np + 3);
+                        float4 m4 = __ldg(np + 4);
+                        ch = make_int2(__float_as_int(m4.z), __float_as_int(m4.w));
+                        // a hit at exactly best.t with a smaller rank must still be found: prune only on strict >
+                        h0 = cull_child(s0, p0, m4.x, c.o, c.d, inv_dd, slack, best.t, t0);
+                        h1 = cull_child(s1, p1, m4.y, c.o, c.d, inv_dd, slack, best.t, t1);
+                    }
+                    if (COUNT) n_sph += 2;
+                    bool second_first = h1 & (!h0 | (t1 < t0));
+                    int near = second_first ? ch.y : ch.x;
+                    int far = second_first ? ch.x : ch.y;
+                    if (h0 & h1) {
+                        stack[sp++] = far;                           // depth <= RT_STACK_MAX - 2 is guaranteed by the build
+#ifdef RT_PREFETCH_FAR
+                        if (far >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(BOX ? (const void *)(S.bnodes + far) : (const void *)(S.nodes + far)));
+#endif
+                    }
+                    cur = (h0 | h1) ? near : stack[--sp];
+                }
+                nm = __ballot_sync(FULL, cur >= 0);
+                if (__popc(nm) < keep) break;
             }
+        }
+        if (live) {
             // ---- cluster (leaf): linear scan like IntersectRayMesh (raytracer.cpp:136-154), <= RT_LEAF_MAX triangles ----
-            if (!done) {
+            if (cur < 0 && cur != RT_DONE) {
                 uint32_t first = leaf_first(cur), cnt = leaf_count(cur);
                 if (COUNT) n_clu += 1;
                 for (uint32_t k = 0; k < cnt; ++k) {
@@ -225,17 +289,17 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                     float t, v, w;
                     if (tri_test(r, c, t, v, w) && t <= best.t && t < FLT_MAX) {    // t < FLT_MAX: raytracer.cpp:149/220 against { FLT_MAX }
                         uint32_t rk = __ldg(S.tri_rank + ti);
-                        if (t < best.t || rk < best_rank) { best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk; }
+                        if (t < best.t || rk < best_rank) {
+                            best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk;
+                            tcull = t * 1.00001f;
+                        }
                     }
                 }
-                if (kind == 1 && best.tri >= 0) done = true;        // occlusion only needs TraceRay's bool (raytracer.cpp:385)
-                else if (sp == 0) done = true;
-                else cur = stack[--sp];
+                cur = (kind == 1 && best.tri >= 0) ? RT_DONE : stack[--sp];        // occlusion only needs TraceRay's bool (raytracer.cpp:385)
             }
-            if (done) {
+            if (cur == RT_DONE) {
                 if (kind == 0) {
                     W.hits[out_idx] = best;
-                    if (G.enabled && best.tri >= 0) W.closest.d[out_idx] = mk4(c.d, 0.0f);   // wave 0: the shading step reads the direction back
                 } else {
                     bool lit = best.tri < 0 || (kind == 2 && best.t * best.t <= dist_sq);   // raytracer.cpp:385 / 395-396
                     if (lit) {
