@@ -227,8 +227,9 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     uint32_t kept_nodes = 0, depth = 0, iterations = 0;
     int32_t root_temp = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n); mode 2 = surface-area search cost (experiment knob)
-        const int pair_mode = attempt ? 1 : (getenv("RT_B200_PLOC_AREA") ? 2 : 0);
+        // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n); mode 2 = surface-area search cost (default; RT_B200_PLOC_COST=diagonal: the squared-diagonal cost)
+        const char *pc = getenv("RT_B200_PLOC_COST");
+        const int pair_mode = attempt ? 1 : ((pc && strcmp(pc, "diagonal") == 0) ? 0 : 2);
         k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, tri_lo, tri_hi, tri_nrm0, tri_slab, cn[0], t); CKLB("k_ploc_init");
         uint32_t m = n, created = 0;
         int cur = 0;

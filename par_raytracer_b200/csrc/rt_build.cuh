@@ -280,8 +280,10 @@ __global__ void k_ploc_init(uint32_t n, const uint32_t *sorted_tri, const float4
     t.nsum[i] = tri_nrm[j]; t.slab[i] = tri_slab[j];
 }
 
-// Search cost = squared diagonal of the merged bounds, i.e. (2 x radius)^2 of the sphere around the merged box:
-// the reference's "smallest parent radius" criterion (bsphere.cpp:295-299) on exact extents instead of on spheres of spheres.
+// Search cost of a candidate pair = size of the merged bounds: mode 0 = squared diagonal, i.e. (2 x radius)^2 of the sphere around the
+// merged box -- the reference's "smallest parent radius" criterion (bsphere.cpp:295-299) on exact extents instead of on spheres of
+// spheres; mode 2 (default) = half surface area of the merged box, the right measure once the traversal bound is the box itself
+// (measured: 2-4 % fewer node visits, profiles/README.md); mode 1 = strict pairing fallback for over-deep trees.
 __global__ void __launch_bounds__(256) k_ploc_nn(uint32_t m, const int32_t *cl_node, TempTree t, uint32_t *nn, int pair_mode) {
     __shared__ float4 slo[256 + 2 * PLOC_RADIUS];
     __shared__ float4 shi[256 + 2 * PLOC_RADIUS];

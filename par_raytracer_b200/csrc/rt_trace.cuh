@@ -139,7 +139,7 @@ RT_DEVICE bool box_child(float lx, float ly, float lz, float hx, float hy, float
 #define RT_FETCH_MIN 16
 #endif
 #ifndef RT_LEAF_WAIT
-#define RT_LEAF_WAIT 32
+#define RT_LEAF_WAIT 12
 #endif
 #define RT_DONE ((int)0x80000000)      // never a leaf ref: |leaf ref| <= 1 + 8 * 2e8 + 7 < 2^31
 
