@@ -114,7 +114,7 @@ struct rt_scene {
     size_t tev_used = 0;
     std::vector<std::pair<uint64_t, uint64_t>> wave_log;   // (closest, shadow) rays per issued wave, aligned with tev (RT_B200_WAVE_LOG=1)
     int sm_count = 148;
-    bool box_bounds = true;              // child bound of the traversal: axis-aligned boxes (default) or sphere + slab (RT_B200_BOUNDS=sphere)
+    int bounds = RT_BOUNDS_QBOX;         // child bound of the traversal: quantised boxes (default), float boxes or sphere + slab (RT_B200_BOUNDS)
     int trace_grid = 148 * 8;            // persistent grid of k_trace_wave: resident blocks of the whole chip
     int logic_grid = 148 * 6;            // same for k_logic
 };
@@ -264,14 +264,39 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         if (attempt == 1) return done(fail(RT_ERR_STATE, "hierarchy depth %u exceeds traversal stack", depth));
     }
 
-    HNode *nodes; BNode *bnodes;
-    CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes))); CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes)));
+    HNode *nodes; BNode *bnodes; QNode *qnodes;
+    CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes))); CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes))); CKB(sc->mem.alloc(&qnodes, std::max(1u, kept_nodes)));
+    // quantisation grid of QNode: 32766 steps across the root box, one step of margin below it
+    double qb[3] = {0, 0, 0}, qs[3] = {1, 1, 1};
+    if (n >= 1) {
+        float4 rlo, rhi;
+        CKB(cudaMemcpyAsync(&rlo, t.lo + (n_total - 1), sizeof(rlo), cudaMemcpyDeviceToHost, st));
+        CKB(cudaMemcpyAsync(&rhi, t.hi + (n_total - 1), sizeof(rhi), cudaMemcpyDeviceToHost, st));
+        CKB(cudaStreamSynchronize(st));
+        const float lo3[3] = {rlo.x, rlo.y, rlo.z}, hi3[3] = {rhi.x, rhi.y, rhi.z};
+        for (int a = 0; a < 3; ++a) {
+            const double lo = lo3[a], hi = hi3[a];
+            float step = (float)std::max((hi - lo) / 32764.0, 1e-30);
+            if (!(step > 0.0f)) step = 1e-30f;
+            // The kernel decodes plane q as qmid + (32768 + q) * qstep from these two FLOATS, so the grid is built from exactly them.
+            // A scene far from the origin relative to its size rounds qmid coarsely: widen the step until the grid covers [lo, hi].
+            for (int it = 0; it < 200; ++it) {
+                const float mid = (float)(lo - (double)step - 32768.0 * (double)step);
+                qs[a] = (double)step;
+                qb[a] = (double)mid + 32768.0 * qs[a];
+                sc->d.qstep[a] = step; sc->d.qmid[a] = mid;
+                if (qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi) break;
+                step *= 1.25f;
+            }
+            if (!(qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi)) return done(fail(RT_ERR_STATE, "cannot place the quantisation grid on axis %d", a));
+        }
+    }
     if (n > 1) {
         k_slot_to_tri<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_offset, slot_tri); CKLB("k_slot_to_tri");
         k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit");
     }
     if (kept_nodes > 0) {
-        k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes, bnodes); CKLB("k_emit_nodes");
+        k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes, bnodes, qnodes, qb[0], qb[1], qb[2], qs[0], qs[1], qs[2]); CKLB("k_emit_nodes");
         sc->d.root = 0;
     } else {
         sc->d.root = -(int)(1u + 0u * 8u + n);     // the whole scene is one cluster (n <= RT_LEAF_MAX)
@@ -284,7 +309,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     CKB(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 
-    sc->d.nodes = nodes; sc->d.bnodes = bnodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
+    sc->d.nodes = nodes; sc->d.bnodes = bnodes; sc->d.qnodes = qnodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
     sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object;
     sc->d.n_tris = n; sc->d.n_nodes = kept_nodes;
     {   // every sphere lies inside the root sphere: |c|_1 + r <= |c_root|_1 + sqrt(3) * 2 r_root + r_root
@@ -293,7 +318,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         sc->d.cull_bound = fabsf(rs.x) + fabsf(rs.y) + fabsf(rs.z) + 4.5f * rs.w;
     }
     sc->info[0] = n; sc->info[1] = 0; sc->info[2] = kept_nodes; sc->info[3] = depth;
-    sc->info[4] = (uint64_t)kept_nodes * (sc->box_bounds ? sizeof(BNode) : sizeof(HNode)); sc->info[5] = (uint64_t)n * sizeof(TriRec);
+    sc->info[4] = (uint64_t)kept_nodes * (sc->bounds == RT_BOUNDS_QBOX ? sizeof(QNode) : sc->bounds == RT_BOUNDS_BOX ? sizeof(BNode) : sizeof(HNode)); sc->info[5] = (uint64_t)n * sizeof(TriRec);
     sc->info[6] = (uint64_t)(ms * 1000.0f); sc->info[7] = iterations;
     return done(RT_OK);
 #undef CKB
@@ -364,10 +389,11 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     CKS(cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, device));
     {
         int per_sm = 0;
-        const char *be = getenv("RT_B200_BOUNDS");      // "sphere": the sphere + slab child bound (kept for the comparison in profiles/)
-        sc->box_bounds = !(be && strcmp(be, "sphere") == 0);
-        if (sc->box_bounds) CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, true>, RT_TRACE_BLOCK, 0));
-        else CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, false>, RT_TRACE_BLOCK, 0));
+        const char *be = getenv("RT_B200_BOUNDS");      // "box" / "sphere": the float-box and sphere + slab child bounds (kept for the comparison in profiles/)
+        sc->bounds = (be && strcmp(be, "sphere") == 0) ? RT_BOUNDS_SPHERE : (be && strcmp(be, "box") == 0) ? RT_BOUNDS_BOX : RT_BOUNDS_QBOX;
+        if (sc->bounds == RT_BOUNDS_QBOX) CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_QBOX>, RT_TRACE_BLOCK, 0));
+        else if (sc->bounds == RT_BOUNDS_BOX) CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_BOX>, RT_TRACE_BLOCK, 0));
+        else CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_SPHERE>, RT_TRACE_BLOCK, 0));
         sc->trace_grid = sc->sm_count * std::max(1, per_sm);
         CKS(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_logic, 128, 0));
         sc->logic_grid = sc->sm_count * std::max(1, per_sm) * 2;
@@ -635,13 +661,12 @@ static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, cons
     cudaStream_t st = sc->stream;
     CK(cudaMemsetAsync(w.next, 0, 4, st));
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sc->trace_grid, std::max<uint64_t>(1, (work_bound + RT_TRACE_BLOCK - 1) / RT_TRACE_BLOCK));
-    if (sc->box_bounds) {
-        if (count) k_trace_wave<true, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
-        else k_trace_wave<false, true><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
-    } else {
-        if (count) k_trace_wave<true, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
-        else k_trace_wave<false, false><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc);
-    }
+#define RT_TRACE_LAUNCH(B) do { if (count) k_trace_wave<true, B><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc); \
+                                else k_trace_wave<false, B><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc); } while (0)
+    if (sc->bounds == RT_BOUNDS_QBOX) RT_TRACE_LAUNCH(RT_BOUNDS_QBOX);
+    else if (sc->bounds == RT_BOUNDS_BOX) RT_TRACE_LAUNCH(RT_BOUNDS_BOX);
+    else RT_TRACE_LAUNCH(RT_BOUNDS_SPHERE);
+#undef RT_TRACE_LAUNCH
     CKL("k_trace_wave");
     return RT_OK;
 }

@@ -15,9 +15,6 @@
 #pragma once
 #include "rt_common.cuh"
 
-#ifndef RT_LEAF_MAX
-#define RT_LEAF_MAX 4
-#endif
 #ifndef PLOC_RADIUS
 #define PLOC_RADIUS 16
 #endif
@@ -417,7 +414,7 @@ __global__ void __launch_bounds__(256) k_refit(uint32_t n, uint32_t n_total, Tem
 }
 
 __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, const uint32_t *tri_offset, const uint32_t *kept_index,
-                             HNode *nodes, BNode *bnodes) {
+                             HNode *nodes, BNode *bnodes, QNode *qnodes, double qbx, double qby, double qbz, double qsx, double qsy, double qsz) {
     uint32_t v = n + blockIdx.x * blockDim.x + threadIdx.x;   // internal temp nodes only
     if (v >= n_nodes_total) return;
     if (t.size[v] <= RT_LEAF_MAX) return;
@@ -431,6 +428,15 @@ __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, con
         q.c1 = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
         q.pad0 = q.pad1 = 0;
         bnodes[kept_index[v]] = q;
+        // 15-bit grid: lo -> floor, hi -> ceil, in double so that the grid plane is never inside the exact extent
+        QNode z;
+        auto ql = [](float x, double b, double st) { double g = floor(((double)x - b) / st); return (uint32_t)fmin(fmax(g, 0.0), 32767.0); };
+        auto qh = [](float x, double b, double st) { double g = ceil(((double)x - b) / st); return (uint32_t)fmin(fmax(g, 0.0), 32767.0); };
+        z.w[0] = ql(la.x, qbx, qsx) | (qh(ha.x, qbx, qsx) << 16); z.w[1] = ql(la.y, qby, qsy) | (qh(ha.y, qby, qsy) << 16);
+        z.w[2] = ql(la.z, qbz, qsz) | (qh(ha.z, qbz, qsz) << 16); z.w[3] = (uint32_t)q.c0;
+        z.w[4] = ql(lb.x, qbx, qsx) | (qh(hb.x, qbx, qsx) << 16); z.w[5] = ql(lb.y, qby, qsy) | (qh(hb.y, qby, qsy) << 16);
+        z.w[6] = ql(lb.z, qbz, qsz) | (qh(hb.z, qbz, qsz) << 16); z.w[7] = (uint32_t)q.c1;
+        qnodes[kept_index[v]] = z;
     }
     o.s0 = t.sphere[a]; o.s1 = t.sphere[b];
     o.p0 = t.slab[a]; o.p1 = t.slab[b];

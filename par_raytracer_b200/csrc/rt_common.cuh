@@ -70,6 +70,17 @@ struct __align__(16) BNode {
 };
 static_assert(sizeof(BNode) == 64, "BNode");
 
+// Quantised form (default): both child boxes on a 15-bit grid spanning the scene bounds, 32 bytes = TWO 16-byte loads per node
+// visit. The trace kernel is bound by L1 wavefronts of scattered node loads (ncu: l1tex data-pipe 73 % busy), so bytes per visit
+// are what count. Grid: world = qbase + q * qstep per axis, q in [0, 32767]; lo rounded down, hi rounded up (conservative).
+//   w[0..2] = child 0: per axis (q_lo | q_hi << 16);  w[3] = child 0 ref;  w[4..6] = child 1;  w[7] = child 1 ref
+struct __align__(16) QNode { uint32_t w[8]; };
+static_assert(sizeof(QNode) == 32, "QNode");
+
+#ifndef RT_LEAF_MAX
+#define RT_LEAF_MAX 4            // triangles per cluster (leaf): subtrees of <= RT_LEAF_MAX triangles collapse into one cluster
+#endif
+
 RT_DEVICE int leaf_ref(uint32_t first, uint32_t count) { return -(int)(1u + first * 8u + count); }
 RT_DEVICE uint32_t leaf_first(int ref) { return ((uint32_t)(-ref) - 1u) >> 3; }
 RT_DEVICE uint32_t leaf_count(int ref) { return ((uint32_t)(-ref) - 1u) & 7u; }
@@ -103,7 +114,10 @@ struct DevLight {             // scene.h:9-15
 
 struct DevScene {
     const HNode *nodes;            // sphere + slab child bounds (RT_B200_BOUNDS=sphere)
-    const BNode *bnodes;           // axis-aligned child bounds (default)
+    const BNode *bnodes;           // axis-aligned child bounds, full floats (RT_B200_BOUNDS=box)
+    const QNode *qnodes;           // axis-aligned child bounds on the 15-bit scene grid (default)
+    float qmid[3];                 // qbase - 32768 * qstep per axis (the decode offset, see qbox_ray_setup)
+    float qstep[3];
     const TriRec *tris;
     const uint32_t *tri_rank;      // tie-break rank: position in the reference's leaf visit order
     const float4 *tri_uv;          // 2 per triangle: (u0 v0 u1 v1) (u2 v2 material_bits -)

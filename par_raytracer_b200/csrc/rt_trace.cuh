@@ -120,6 +120,45 @@ RT_DEVICE bool box_child(float lx, float ly, float lz, float hx, float hy, float
     return tn <= tf;
 }
 
+// ---- quantised child bounds (default) ------------------------------------------------------------------------
+// Same slab test on QNode's 15-bit grid. A grid coordinate q becomes the float 0.5 + q 2^-16 with ONE byte permute
+// (bytes 0x3F, q.hi, q.lo, 0x00), and plane parameter t = (qmid + 32768 step + q step - o) / d = qf * A + C with per-ray
+// A = 65536 step / d and C = (qmid - o) / d: one PRMT + one FMA per plane. The permute selector picks the lo or the hi half of the
+// axis word, so the ray's direction signs choose near and far planes up front and the per-axis min / max disappears: a node
+// visit costs about what the float-box visit costs, with half the bytes and half the load instructions. The per-ray slack
+// moves the near plane towards the origin side and the far plane away from it (cn / cf), as in box_ray_setup.
+#define RT_BOUNDS_SPHERE 0
+#define RT_BOUNDS_BOX 1
+#define RT_BOUNDS_QBOX 2
+struct QRay { float ax, ay, az, cnx, cny, cnz, cfx, cfy, cfz; uint32_t snx, sny, snz; };   // s?: near selector; far = near ^ 0x0220
+
+RT_DEVICE void qbox_ray_setup(QRay &Q, const DevScene &S, f3 o, f3 d, float slack) {
+    float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
+    float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
+    float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+    float ix = approx_rcp(dx), iy = approx_rcp(dy), iz = approx_rcp(dz);
+    bool px = !signbit(dx), py = !signbit(dy), pz = !signbit(dz);
+    Q.ax = 65536.0f * S.qstep[0] * ix; Q.ay = 65536.0f * S.qstep[1] * iy; Q.az = 65536.0f * S.qstep[2] * iz;
+    float sx = px ? slack : -slack, sy = py ? slack : -slack, sz = pz ? slack : -slack;
+    Q.cnx = (S.qmid[0] - (o.x + sx)) * ix; Q.cfx = (S.qmid[0] - (o.x - sx)) * ix;
+    Q.cny = (S.qmid[1] - (o.y + sy)) * iy; Q.cfy = (S.qmid[1] - (o.y - sy)) * iy;
+    Q.cnz = (S.qmid[2] - (o.z + sz)) * iz; Q.cfz = (S.qmid[2] - (o.z - sz)) * iz;
+    Q.snx = px ? 0x7104u : 0x7324u; Q.sny = py ? 0x7104u : 0x7324u; Q.snz = pz ? 0x7104u : 0x7324u;
+}
+
+RT_DEVICE bool qbox_child(uint32_t wx, uint32_t wy, uint32_t wz, const QRay &Q, float tmax, float &tn) {
+    const uint32_t K = 0x3F000000u;
+    float tnx = __fmaf_rn(__uint_as_float(__byte_perm(wx, K, Q.snx)), Q.ax, Q.cnx);
+    float tny = __fmaf_rn(__uint_as_float(__byte_perm(wy, K, Q.sny)), Q.ay, Q.cny);
+    float tnz = __fmaf_rn(__uint_as_float(__byte_perm(wz, K, Q.snz)), Q.az, Q.cnz);
+    float tfx = __fmaf_rn(__uint_as_float(__byte_perm(wx, K, Q.snx ^ 0x0220u)), Q.ax, Q.cfx);
+    float tfy = __fmaf_rn(__uint_as_float(__byte_perm(wy, K, Q.sny ^ 0x0220u)), Q.ay, Q.cfy);
+    float tfz = __fmaf_rn(__uint_as_float(__byte_perm(wz, K, Q.snz ^ 0x0220u)), Q.az, Q.cfz);
+    tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+    float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    return tn <= tf;
+}
+
 // ---- the wave trace kernel -----------------------------------------------------------------------------
 // One launch traces everything a wave has to trace: the closest-hit rays of the pending recursion nodes AND the
 // shadow rays queued by the previous shading step (ShadeLight, raytracer.cpp:378-411), so a wave pays one
@@ -132,9 +171,13 @@ RT_DEVICE bool box_child(float lx, float ly, float lz, float hx, float hy, float
 // while-while loop: descend internal nodes nearest-child first, then scan the reached cluster. stack[0] holds a
 // sentinel, so "pop" needs no emptiness test: popping the sentinel ends the ray.
 //
-// BOX selects the child bound: axis-aligned boxes (64-byte nodes, ~50 instructions per node visit) or the sphere + slab
-// bound (80-byte nodes, ~105 instructions per visit); both are conservative, so hits are identical (tests run both).
+// BOUNDS selects the child bound: axis-aligned boxes on the 15-bit scene grid (32-byte nodes, 2 loads per visit; default),
+// float boxes (64-byte nodes, 4 loads, ~60 instructions per visit) or the sphere + slab bound (80-byte nodes, 5 loads, ~105
+// instructions per visit). All are conservative, so hits are identical (tests run all three).
 #define RT_TRACE_BLOCK 128
+#ifndef RT_TRACE_MIN_BLOCKS
+#define RT_TRACE_MIN_BLOCKS 8          // 64 registers per thread: 32 warps per SM
+#endif
 #ifndef RT_FETCH_MIN
 #define RT_FETCH_MIN 16
 #endif
@@ -162,8 +205,8 @@ struct WaveQueues {
     uint32_t leaf_wait;            // leave the node loop once this many live lanes wait at a cluster / have finished (32: only when all do)
 };
 
-template <bool COUNT, bool BOX>
-__global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float bias, WaveQueues W, PrimaryGen G, TraceCounters *counters) {
+template <bool COUNT, int BOUNDS>
+__global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_wave(DevScene S, float bias, WaveQueues W, PrimaryGen G, TraceCounters *counters) {
     const uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t nC = G.enabled ? G.n_slots : (W.n_closest ? min(*W.n_closest, W.closest_max) : W.closest_max);
@@ -174,13 +217,17 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
     bool live = false, exhausted = false;
     uint32_t fetch_min = G.enabled ? W.fetch_min_primary : W.fetch_min;
     RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
+    constexpr bool BOX = BOUNDS == RT_BOUNDS_BOX, QBOX = BOUNDS == RT_BOUNDS_QBOX;
     BoxRay R; R.ix = R.iy = R.iz = R.clx = R.cly = R.clz = R.chx = R.chy = R.chz = 0.0f;
+    QRay Q; Q.ax = Q.ay = Q.az = Q.cnx = Q.cny = Q.cnz = Q.cfx = Q.cfy = Q.cfz = 0.0f; Q.snx = Q.sny = Q.snz = 0x7104u;
     float inv_dd = 0.0f, dist_sq = -1.0f, slack = 0.0f;
     HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
-    float tcull = FLT_MAX;         // BOX: best.t widened by 1e-5 relative, so a box entered a few ulps beyond best.t is still opened
+    float tcull = FLT_MAX;         // boxes: best.t widened by 1e-5 relative, so a box entered a few ulps beyond best.t is still opened
     uint32_t best_rank = 0xFFFFFFFFu, out_idx = 0, light = 0;
     int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light)
-    int cur = RT_DONE, sp = 1;
+    // Traversal stack: the logical top lives in the register `top`, the rest in local memory (stack[0] = sentinel). A pop takes
+    // the register and issues the reload of the next entry at once, so the load latency is off the critical path of the descent.
+    int cur = RT_DONE, sp = 1, top = RT_DONE;
     int stack[RT_STACK_MAX];
     stack[0] = RT_DONE;
 
@@ -224,11 +271,12 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                     f3 q = c.o + dir;
                     c.qp = c.o - q;
                     slack = RT_CULL_SLACK * (fabsf(c.o.x) + fabsf(c.o.y) + fabsf(c.o.z) + S.cull_bound);
-                    if (BOX) box_ray_setup(R, c.o, dir, slack);
+                    if (QBOX) qbox_ray_setup(Q, S, c.o, dir, slack);
+                    else if (BOX) box_ray_setup(R, c.o, dir, slack);
                     else { c.d = dir; inv_dd = approx_rcp(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x))); }   // culling only
                     best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1; best_rank = 0xFFFFFFFFu;   // raytracer.cpp:166
                     tcull = FLT_MAX;
-                    cur = S.n_tris ? S.root : RT_DONE; sp = 1;
+                    cur = S.n_tris ? S.root : RT_DONE; sp = 1; top = RT_DONE;
                     live = true;
                 }
             }
@@ -246,7 +294,13 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
             while (nm != 0) {
                 if (cur >= 0) {
                     int2 ch; bool h0, h1; float t0, t1;
-                    if (BOX) {
+                    if (QBOX) {
+                        const uint4 *np = reinterpret_cast<const uint4 *>(S.qnodes + cur);
+                        uint4 A = __ldg(np), B = __ldg(np + 1);
+                        ch = make_int2((int)A.w, (int)B.w);
+                        h0 = qbox_child(A.x, A.y, A.z, Q, tcull, t0);
+                        h1 = qbox_child(B.x, B.y, B.z, Q, tcull, t1);
+                    } else if (BOX) {
                         const float4 *np = reinterpret_cast<const float4 *>(S.bnodes + cur);
                         float4 A = __ldg(np), B = __ldg(np + 1), C = __ldg(np + 2);
                         ch = __ldg(reinterpret_cast<const int2 *>(np + 3));
@@ -266,12 +320,13 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
                     int near = second_first ? ch.y : ch.x;
                     int far = second_first ? ch.x : ch.y;
                     if (h0 & h1) {
-                        stack[sp++] = far;                           // depth <= RT_STACK_MAX - 2 is guaranteed by the build
+                        stack[sp++] = top; top = far;                // depth <= RT_STACK_MAX - 2 is guaranteed by the build
 #ifdef RT_PREFETCH_FAR
-                        if (far >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(BOX ? (const void *)(S.bnodes + far) : (const void *)(S.nodes + far)));
+                        if (far >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(QBOX ? (const void *)(S.qnodes + far) : BOX ? (const void *)(S.bnodes + far) : (const void *)(S.nodes + far)));
 #endif
                     }
-                    cur = (h0 | h1) ? near : stack[--sp];
+                    if (h0 | h1) cur = near;
+                    else { cur = top; top = stack[--sp]; }
                 }
                 nm = __ballot_sync(FULL, cur >= 0);
                 if (__popc(nm) < keep) break;
@@ -282,20 +337,47 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK) k_trace_wave(DevScene S, float
             if (cur < 0 && cur != RT_DONE) {
                 uint32_t first = leaf_first(cur), cnt = leaf_count(cur);
                 if (COUNT) n_clu += 1;
-                for (uint32_t k = 0; k < cnt; ++k) {
-                    uint32_t ti = first + k;
-                    const float4 *tp = reinterpret_cast<const float4 *>(S.tris + ti);
-                    TriRec r; r.r0 = __ldg(tp); r.r1 = __ldg(tp + 1); r.r2 = __ldg(tp + 2);
-                    float t, v, w;
-                    if (tri_test(r, c, t, v, w) && t <= best.t && t < FLT_MAX) {    // t < FLT_MAX: raytracer.cpp:149/220 against { FLT_MAX }
-                        uint32_t rk = __ldg(S.tri_rank + ti);
-                        if (t < best.t || rk < best_rank) {
-                            best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk;
-                            tcull = t * 1.00001f;
+                // The first record word (normal + a.x) of every triangle of the cluster is requested before the first test: one
+                // memory latency per cluster instead of one per triangle, and those loads pull in most 32-byte sectors of the
+                // cluster's 48-byte records, so the remaining words of a front-facing triangle are mostly L1 hits.
+                // Arithmetic = tri_test, same order.
+                const float4 *tp = reinterpret_cast<const float4 *>(S.tris + first);
+                float4 r0[RT_LEAF_MAX];
+#pragma unroll
+                for (int k = 0; k < RT_LEAF_MAX; ++k) if (k < (int)cnt) r0[k] = __ldg(tp + 3 * k);
+#pragma unroll
+                for (int k = 0; k < RT_LEAF_MAX; ++k) {
+                    if (k < (int)cnt) {
+                        f3 n = mk3(r0[k].x, r0[k].y, r0[k].z);
+                        float dd = dot3(c.qp, n);
+                        if (!(dd <= 0.0f)) {                                        // raytracer.cpp:97-98
+                            float4 r1 = __ldg(tp + 3 * k + 1), r2 = __ldg(tp + 3 * k + 2);
+                            f3 ap = c.o - mk3(r0[k].w, r1.x, r1.y);
+                            float t = dot3(ap, n);
+                            if (!(t < 0.0f)) {                                      // raytracer.cpp:102-103
+                                f3 e = cross3(c.qp, ap);
+                                float v = dot3(mk3(r2.y, r2.z, r2.w), e);
+                                if (!(v < 0.0f || v > dd)) {                        // raytracer.cpp:108-109
+                                    float w = -dot3(mk3(r1.z, r1.w, r2.x), e);
+                                    if (!(w < 0.0f || (v + w) > dd)) {              // raytracer.cpp:110-111
+                                        float ood = 1.0f / dd;
+                                        t = t * ood; v = v * ood; w = w * ood;
+                                        if (t <= best.t && t < FLT_MAX) {           // t < FLT_MAX: raytracer.cpp:149/220 against { FLT_MAX }
+                                            uint32_t ti = first + (uint32_t)k;
+                                            uint32_t rk = __ldg(S.tri_rank + ti);
+                                            if (t < best.t || rk < best_rank) {
+                                                best.t = t; best.v = v; best.w = w; best.tri = (int32_t)ti; best_rank = rk;
+                                                tcull = t * 1.00001f;
+                                            }
+                                        }
+                                    }
+                                }
+                            }
                         }
                     }
                 }
-                cur = (kind == 1 && best.tri >= 0) ? RT_DONE : stack[--sp];        // occlusion only needs TraceRay's bool (raytracer.cpp:385)
+                if (kind == 1 && best.tri >= 0) cur = RT_DONE;                     // occlusion only needs TraceRay's bool (raytracer.cpp:385)
+                else { cur = top; top = stack[--sp]; }
             }
             if (cur == RT_DONE) {
                 if (kind == 0) {
