@@ -264,8 +264,11 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         if (attempt == 1) return done(fail(RT_ERR_STATE, "hierarchy depth %u exceeds traversal stack", depth));
     }
 
-    HNode *nodes; BNode *bnodes; QNode *qnodes;
-    CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes))); CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes))); CKB(sc->mem.alloc(&qnodes, std::max(1u, kept_nodes)));
+    // only the node array of the selected child bound is built (RT_B200_BOUNDS)
+    HNode *nodes = nullptr; BNode *bnodes = nullptr; QNode *qnodes = nullptr;
+    if (sc->bounds == RT_BOUNDS_SPHERE) CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
+    else if (sc->bounds == RT_BOUNDS_BOX) CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes)));
+    else CKB(sc->mem.alloc(&qnodes, std::max(1u, kept_nodes)));
     // quantisation grid of QNode: 32766 steps across the root box, one step of margin below it
     double qb[3] = {0, 0, 0}, qs[3] = {1, 1, 1};
     if (n >= 1) {
@@ -293,7 +296,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     }
     if (n > 1) {
         k_slot_to_tri<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_offset, slot_tri); CKLB("k_slot_to_tri");
-        k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit");
+        if (sc->bounds == RT_BOUNDS_SPHERE) { k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit"); }
     }
     if (kept_nodes > 0) {
         k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes, bnodes, qnodes, qb[0], qb[1], qb[2], qs[0], qs[1], qs[2]); CKLB("k_emit_nodes");

@@ -418,16 +418,16 @@ __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, con
     uint32_t v = n + blockIdx.x * blockDim.x + threadIdx.x;   // internal temp nodes only
     if (v >= n_nodes_total) return;
     if (t.size[v] <= RT_LEAF_MAX) return;
-    HNode o;
     int32_t a = t.c0[v], b = t.c1[v];
-    {
+    const int32_t ref_a = t.size[a] > RT_LEAF_MAX ? (int32_t)kept_index[a] : leaf_ref(tri_offset[a], t.size[a]);
+    const int32_t ref_b = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
+    if (bnodes || qnodes) {
         float4 la = t.lo[a], ha = t.hi[a], lb = t.lo[b], hb = t.hi[b];      // exact vertex extents; the traversal pads them per ray
         BNode q;
         q.a = make_float4(la.x, la.y, la.z, ha.x); q.b = make_float4(ha.y, ha.z, lb.x, lb.y); q.c = make_float4(lb.z, hb.x, hb.y, hb.z);
-        q.c0 = t.size[a] > RT_LEAF_MAX ? (int32_t)kept_index[a] : leaf_ref(tri_offset[a], t.size[a]);
-        q.c1 = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
+        q.c0 = ref_a; q.c1 = ref_b;
         q.pad0 = q.pad1 = 0;
-        bnodes[kept_index[v]] = q;
+        if (bnodes) bnodes[kept_index[v]] = q;
         // 15-bit grid: lo -> floor, hi -> ceil, in double so that the grid plane is never inside the exact extent
         QNode z;
         auto ql = [](float x, double b, double st) { double g = floor(((double)x - b) / st); return (uint32_t)fmin(fmax(g, 0.0), 32767.0); };
@@ -436,13 +436,14 @@ __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, con
         z.w[2] = ql(la.z, qbz, qsz) | (qh(ha.z, qbz, qsz) << 16); z.w[3] = (uint32_t)q.c0;
         z.w[4] = ql(lb.x, qbx, qsx) | (qh(hb.x, qbx, qsx) << 16); z.w[5] = ql(lb.y, qby, qsy) | (qh(hb.y, qby, qsy) << 16);
         z.w[6] = ql(lb.z, qbz, qsz) | (qh(hb.z, qbz, qsz) << 16); z.w[7] = (uint32_t)q.c1;
-        qnodes[kept_index[v]] = z;
+        if (qnodes) qnodes[kept_index[v]] = z;
     }
+    if (!nodes) return;
+    HNode o;
     o.s0 = t.sphere[a]; o.s1 = t.sphere[b];
     o.p0 = t.slab[a]; o.p1 = t.slab[b];
     o.dmax0 = t.nsum[a].w; o.dmax1 = t.nsum[b].w;
-    o.c0 = t.size[a] > RT_LEAF_MAX ? (int32_t)kept_index[a] : leaf_ref(tri_offset[a], t.size[a]);
-    o.c1 = t.size[b] > RT_LEAF_MAX ? (int32_t)kept_index[b] : leaf_ref(tri_offset[b], t.size[b]);
+    o.c0 = ref_a; o.c1 = ref_b;
     nodes[kept_index[v]] = o;
 }
 

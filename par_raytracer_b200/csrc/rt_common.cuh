@@ -26,11 +26,15 @@ RT_DEVICE float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  
 RT_DEVICE f3 cross3(f3 a, f3 b) {                                                // mathlib.h:239-246
     return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
 }
+// IEEE x / l for l > 0. A zero numerator sends CUDA's div.rn into its out-of-line slow path (~35 instructions + call; ncu showed
+// 15 % of k_logic's instructions there: the tangent frames of raytracer.cpp:306-312 always carry an exact 0 component). 0 / l is the
+// numerator itself (sign kept) for every l that is not NaN, so that case is answered without dividing -- same bits.
+RT_DEVICE float div_pos(float x, float l) { return (x == 0.0f && l == l) ? x : x / l; }
 RT_DEVICE f3 normalize3(f3 a) {                                                  // mathlib.h:253-262
     float l2 = dot3(a, a);
     if (l2 == 0.0f) return a;
     float l = sqrtf(l2);
-    return mk3(a.x / l, a.y / l, a.z / l);
+    return mk3(div_pos(a.x, l), div_pos(a.y, l), div_pos(a.z, l));
 }
 RT_DEVICE float max0(float x) { return 0.0f > x ? 0.0f : x; }                    // Max(0.0f, x), mathlib.h:8
 RT_DEVICE float clampf(float n, float a, float b) {                              // Clamp, mathlib.h:9

@@ -164,10 +164,15 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
     const uint32_t n_in = G.enabled ? G.n_slots : min(*n_in_ptr, n_in_max);
     const uint32_t cap = P.capacity;
     const int bd = (int)prm.bounce_depth;
-    // persistent blocks, block-uniform trip count (every lane of a warp reaches the warp-aggregated pushes together)
+    // persistent blocks, block-uniform trip count (every lane of a warp reaches the warp-aggregated pushes together); the hit record
+    // of the NEXT trip is requested at the top of the current one (the first, otherwise fully exposed, load of a trip)
+    HitRec h_next; h_next.t = 0.0f; h_next.v = 0.0f; h_next.w = 0.0f; h_next.tri = -1;
+    if (blockIdx.x * blockDim.x + threadIdx.x < n_in) h_next = hits[blockIdx.x * blockDim.x + threadIdx.x];
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_in; base += gridDim.x * blockDim.x) {
     uint32_t i = base + threadIdx.x;
     bool active = i < n_in;
+    const HitRec h_cur = h_next;
+    { uint64_t in = (uint64_t)i + (uint64_t)gridDim.x * blockDim.x; if (in < n_in) h_next = hits[in]; }
 
     uint32_t slot = 0, sp = 0;
     int iters = 0;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
     float spec_int = 0.0f, w_diffuse = 0.0f;
 
     if (active) {
-        HitRec h = hits[i];
+        const HitRec h = h_cur;
         f3 org;
         if (G.enabled) {
             // wave 0: the primary ray and the fresh path state are recomputed, not streamed (rt_raygen.cuh); a primary
@@ -300,6 +305,7 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
     for (uint32_t l = 0; l < S.n_lights; ++l) {
         f3 rad = mk3(0, 0, 0);
         float dist_sq = -1.0f;
+        const uint32_t spos = warp_push(sh.count + l, shade_hit) + l * sh.capacity;     // issued first: the atomic's latency hides under the shading math
         if (shade_hit) {
             DevLight L = S.lights[l];
             f3 lc = mk3(L.color[0], L.color[1], L.color[2]);
@@ -319,7 +325,6 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             f3 ds = lc * phong_pow(max0(spec_cos), spec_int);
             rad = Ta * (((dd * kd) * w_diffuse) + ds * ks);                  // raytracer.cpp:544-545
         }
-        uint32_t spos = warp_push(sh.count + l, shade_hit) + l * sh.capacity;
         if (shade_hit) {
             sh.o[spos] = mk4u(hit_p, slot);
             sh.rad[spos] = mk4(rad, dist_sq);
@@ -371,6 +376,10 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             if (rng_float01(rng) < 0.5f) continue;
             emit = true; e_org = c_org; e_dir = c_dir; e_T = c_T; e_iters = f_iters - 1;
         }
+    }
+    // K6: compaction -- the next wave's queue holds only rays that exist (the atomic is issued before the state stores)
+    uint32_t pos = warp_push(n_out, emit);
+    if (active) {
         P.acc[slot] = mk4(acc, 0.0f);
         if (emit) {                                    // a finished path only leaves its radiance behind
             P.rng_cx[slot] = rng_pack(rng);
@@ -378,9 +387,6 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             if (G.enabled) P.rng_seed[slot] = rng.seed;
         }
     }
-
-    // K6: compaction -- the next wave's queue holds only rays that exist
-    uint32_t pos = warp_push(n_out, emit);
     if (emit) { qout.o[pos] = mk4(e_org, 0.0f); qout.d[pos] = mk4u(e_dir, slot); }
     }
 }

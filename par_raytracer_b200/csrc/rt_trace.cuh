@@ -316,16 +316,16 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                         h1 = cull_child(s1, p1, m4.y, c.o, c.d, inv_dd, slack, best.t, t1);
                     }
                     if (COUNT) n_sph += 2;
-                    bool second_first = h1 & (!h0 | (t1 < t0));
-                    int near = second_first ? ch.y : ch.x;
-                    int far = second_first ? ch.x : ch.y;
-                    if (h0 & h1) {
+                    const bool second_first = h1 && (!h0 || t1 < t0);
+                    const int near = second_first ? ch.y : ch.x;
+                    const int far = second_first ? ch.x : ch.y;
+                    if (h0 && h1) {
                         stack[sp++] = top; top = far;                // depth <= RT_STACK_MAX - 2 is guaranteed by the build
 #ifdef RT_PREFETCH_FAR
                         if (far >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(QBOX ? (const void *)(S.qnodes + far) : BOX ? (const void *)(S.bnodes + far) : (const void *)(S.nodes + far)));
 #endif
                     }
-                    if (h0 | h1) cur = near;
+                    if (h0 || h1) cur = near;
                     else { cur = top; top = stack[--sp]; }
                 }
                 nm = __ballot_sync(FULL, cur >= 0);

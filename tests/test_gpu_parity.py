@@ -167,6 +167,54 @@ def test_seeded_scenes_against_oracle(kind):
     S.close()
 
 
+@pytest.mark.parametrize("bounds", ["qbox", "box", "sphere"])
+def test_child_bound_variants_far_from_origin(bounds, monkeypatch):
+    """The traversal's child bound only prunes, so every variant must give the oracle's hits: 15-bit quantised boxes
+    (default), float boxes, sphere + slab (RT_B200_BOUNDS, read at scene creation). The scene sits ~10^4 units from the
+    origin and is 100 units across: float coordinates there have an ulp of ~1e-3, i.e. comparable to the quantisation
+    step -- the case the grid placement and the per-ray slack have to get right."""
+    import dataclasses
+    monkeypatch.setenv("RT_B200_BOUNDS", bounds)
+    base = scenes.heightfield_scene(64, 48, block=8, textured=False)
+    off = np.array([5000.0, -3000.0, 8000.0], np.float32)
+    sph = base.spheres.copy(); sph["center"] += off
+    sd = dataclasses.replace(base, positions=base.positions + off, spheres=sph)
+    S = api.Scene(sd); O = oracle.OracleScene(sd)
+    assert S.hierarchy_info()["node_bytes"] // max(1, S.hierarchy_info()["nodes"]) == {"qbox": 32, "box": 64, "sphere": 80}[bounds]
+    W, H = 96, 64
+    h = base.camera_hint
+    cam = types.make_camera(h["fov"], W, H, tuple(np.asarray(h["position"], np.float32) + off), h["facing"])
+    p = types.default_params(spp=2, base_seed=0x5EED)
+    rg, hg = S.trace_primary(cam, p, W, H, sample_count=2)
+    ro, ho = O.trace_primary(cam, p, W, H, None, 0, W * H, 0, 2)
+    assert rg.tobytes() == ro.tobytes()
+    assert_hits_equal(hg, ho, bounds + " primary")
+    assert 0.2 < ho["hit"].mean() <= 1.0
+    rng = np.random.default_rng(5)
+    n = 40000
+    rays = np.zeros(n, RAY)
+    lo, hi = sd.positions.min(0), sd.positions.max(0)
+    rays["origin"] = (lo + (hi - lo) * rng.random((n, 3)) + np.array([0, 1.5, 0])).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d[: n // 8, rng.integers(0, 3)] = 0.0                          # rays inside an axis plane: an exact zero direction component
+    d /= np.linalg.norm(d, axis=1, keepdims=True)                  # unit length like every ray of the reference: its own sphere
+    rays["direction"] = d.astype(np.float32)                       # test (raytracer.cpp:32-60) loses hits for |d| < 1
+    tri = rng.integers(0, sd.n_triangles, n // 2)
+    rays["origin"][: n // 2] = sd.positions[sd.idx_positions[3 * tri]]     # rays starting ON the geometry
+    hg2, _ = S.trace_rays(p, rays)
+    ho2, _ = O.trace_rays(p, rays)
+    assert_hits_equal(hg2, ho2, bounds + " random")
+    hb, _ = S.trace_rays(p, rays, api.RT_TRACE_BRUTE)
+    assert_hits_equal(hb, ho2, bounds + " brute")
+    ha, _ = S.trace_rays(p, rays, api.RT_TRACE_ANY)
+    assert np.array_equal(ha["hit"], ho2["hit"])
+    img, cnt = S.render(cam, p, W, H)
+    ref, _, cnt_o, _ = O.render(cam, p, W, H, threads=8)
+    assert cnt["ray_count"] == cnt_o["ray_count"]
+    assert np.allclose(img.reshape(-1, 4), ref, rtol=RTOL, atol=ATOL)
+    S.close()
+
+
 def test_param_variants_against_oracle():
     """bounce depth 0 / 1 / 3, several reflection and specular samples, > 15 draws per sample (ring wrap)."""
     sd = scenes.spheres_plane_scene(grid=2, nu=16, nv=8, textured=True)
