@@ -42,6 +42,7 @@ WORKLOADS = {
     "config2": (1920, 1080, 64, WORKLOAD),
     "config3": (1920, 1080, 128, "config3: procedural height field, 1048352 textured triangles / 529 groups (diffuse, ambient, bump, alpha maps), 1920x1080, 128 spp"),
     "config4": (3840, 2160, 256, "config4: procedural height field, 9999392 triangles / 4900 groups, 3840x2160, 256 spp"),
+    "config5": (1920, 1080, 512, "config5: config-3 scene (1048352 textured triangles), 1920x1080, 512 spp per GPU (4096 spp on 8 GPUs), sample ranges + NCCL reduce of the accumulation frames"),
 }
 
 
@@ -56,6 +57,7 @@ ROOFLINE_NOTE = {
                "(`traffic` / rays per launch) is far BELOW the algorithmic figure and frac can exceed 1: on this scene the kernel is bound by the ALU pipe "
                "(ncu, profiles/: 64-72 % of ALU-pipe peak, 68-77 % issue slots busy, DRAM < 8 %)",
     "config3": "achieved counts SURVEY 8(d)'s algorithmic bytes (904 B per ray); ncu: the kernel waits on scattered node / triangle loads (L1 hit 60-70 %)",
+    "config5": "achieved counts SURVEY 8(d)'s algorithmic bytes (904 B per ray); ncu: the kernel waits on scattered node / triangle loads (L1 hit 60-70 %)",
     "config4": "achieved counts SURVEY 8(d)'s algorithmic bytes (1032 B per ray); ncu (profiles/): 45-50 % of stall samples wait on node and triangle "
                "loads (L1 hit 57-67 %, L2 hit 58-69 %), DRAM 5-11 % of peak: latency of dependent scattered loads, not bandwidth, bounds the kernel",
 }
@@ -209,7 +211,7 @@ def cpu_arm(scene_data, cam, params, budget_s: float, steps: int = 1, warmup: in
 
 def make_inputs():
     from par_raytracer_b200 import scenes, types
-    if WORKLOAD_KEY == "config3":
+    if WORKLOAD_KEY in ("config3", "config5"):
         sd = scenes.heightfield_scene(724, 724, block=32, size=400.0, amp=20.0, textured=True, tex_size=512)
     elif WORKLOAD_KEY == "config4":
         sd = scenes.heightfield_scene(2236, 2236, block=32, size=400.0, amp=20.0, textured=False)
