@@ -264,13 +264,9 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         if (attempt == 1) return done(fail(RT_ERR_STATE, "hierarchy depth %u exceeds traversal stack", depth));
     }
 
-    // only the node array of the selected child bound is built (RT_B200_BOUNDS)
-    HNode *nodes = nullptr; BNode *bnodes = nullptr; QNode *qnodes = nullptr;
-    if (sc->bounds == RT_BOUNDS_SPHERE) CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
-    else if (sc->bounds == RT_BOUNDS_BOX) CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes)));
-    else CKB(sc->mem.alloc(&qnodes, std::max(1u, kept_nodes)));
     // quantisation grid of QNode: 32766 steps across the root box, one step of margin below it
     double qb[3] = {0, 0, 0}, qs[3] = {1, 1, 1};
+    bool grid_ok = true;
     if (n >= 1) {
         float4 rlo, rhi;
         CKB(cudaMemcpyAsync(&rlo, t.lo + (n_total - 1), sizeof(rlo), cudaMemcpyDeviceToHost, st));
@@ -291,9 +287,15 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
                 if (qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi) break;
                 step *= 1.25f;
             }
-            if (!(qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi)) return done(fail(RT_ERR_STATE, "cannot place the quantisation grid on axis %d", a));
+            if (!(qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi)) grid_ok = false;     // non-finite extents: no grid can cover them
         }
     }
+    if (!grid_ok && sc->bounds == RT_BOUNDS_QBOX) sc->bounds = RT_BOUNDS_BOX;   // float boxes need no grid (inf / NaN vertices behave as they do there)
+    // only the node array of the selected child bound is built (RT_B200_BOUNDS)
+    HNode *nodes = nullptr; BNode *bnodes = nullptr; QNode *qnodes = nullptr;
+    if (sc->bounds == RT_BOUNDS_SPHERE) CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
+    else if (sc->bounds == RT_BOUNDS_BOX) CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes)));
+    else CKB(sc->mem.alloc(&qnodes, std::max(1u, kept_nodes)));
     if (n > 1) {
         k_slot_to_tri<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_offset, slot_tri); CKLB("k_slot_to_tri");
         if (sc->bounds == RT_BOUNDS_SPHERE) { k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit"); }
