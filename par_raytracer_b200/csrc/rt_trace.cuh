@@ -1,4 +1,4 @@
-// rt_trace.cuh -- kernel group K3 / K3s: hierarchy traversal + ray/sphere + ray/triangle.
+// rt_trace.cuh -- kernel group K3 / K3s: hierarchy traversal + child-bound test + ray/triangle.
 //
 // Replaces TraceRay (raytracer.cpp:159-232) with its callees IntersectRaySphere (32-60),
 // IntersectRayMesh (127-157) and IntersectRayTriangle (82-125).
@@ -10,9 +10,10 @@
 //    reference's own encounter order (c1-subtree-first DFS over its hierarchy, then index order inside a
 //    group; raytracer.cpp:136, 149, 208-209, 220), so equal-t ties resolve as in the reference although
 //    our traversal order is different.
-//  * The SPHERE test only prunes. It is our own robust formulation (distance from the centre to the ray
-//    line through the perpendicular foot, FMA allowed) with a slack proportional to the distance from
-//    the ray origin, so float rounding can never prune a triangle the exact test would accept.
+//  * The CHILD-BOUND test only prunes (the reference's IntersectRaySphere plays that role there). Three
+//    interchangeable forms -- boxes on a 15-bit grid (default), float boxes, sphere + slab -- all fattened
+//    by a slack proportional to the distance from the ray origin, so float rounding can never prune a
+//    triangle the exact test would accept; FMA and approximate reciprocals are allowed in them.
 #pragma once
 #include "rt_common.cuh"
 #include "rt_raygen.cuh"
@@ -326,9 +327,6 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                     const int far = second_first ? ch.x : ch.y;
                     if (h0 && h1) {
                         stack[sp++] = top; top = far;                // depth <= RT_STACK_MAX - 2 is guaranteed by the build
-#ifdef RT_PREFETCH_FAR
-                        if (far >= 0) asm volatile("prefetch.global.L1 [%0];" :: "l"(QBOX ? (const void *)(S.qnodes + far) : BOX ? (const void *)(S.bnodes + far) : (const void *)(S.nodes + far)));
-#endif
                     }
                     if (h0 || h1) cur = near;
                     else { cur = top; top = stack[--sp]; }
