@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
     constexpr bool BOX = BOUNDS == RT_BOUNDS_BOX, QBOX = BOUNDS == RT_BOUNDS_QBOX;
     BoxRay R; R.ix = R.iy = R.iz = R.clx = R.cly = R.clz = R.chx = R.chy = R.chz = 0.0f;
     QRay Q; Q.ax = Q.ay = Q.az = Q.cnx = Q.cny = Q.cnz = Q.cfx = Q.cfy = Q.cfz = 0.0f; Q.snx = Q.sny = Q.snz = 0x7104u;
-    float inv_dd = 0.0f, dist_sq = -1.0f, slack = 0.0f;
+    float inv_dd = 0.0f, slack = 0.0f;
     HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;
     float tcull = FLT_MAX;         // boxes: best.t widened by 1e-5 relative, so a box entered a few ulps beyond best.t is still opened
-    uint32_t best_rank = 0xFFFFFFFFu, out_idx = 0, light = 0;
-    int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light)
+    uint32_t best_rank = 0xFFFFFFFFu, out_idx = 0;
+    int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light); shadow kinds carry the light index << 2
     // Traversal stack: the logical top lives in the register `top`, the rest in local memory (stack[0] = sentinel). A pop takes
     // the register and issues the reload of the next entry at once, so the load latency is off the critical path of the descent.
     int cur = RT_DONE, sp = 1, top = RT_DONE;
@@ -257,11 +257,11 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                         else { o4 = W.closest.o[idx]; d4 = W.closest.d[idx]; }
                     }
                     else {
-                        uint32_t j = idx - nC; light = 0;
+                        uint32_t j = idx - nC, light = 0;
                         while (true) { uint32_t ns = min(W.n_shadow[light], W.shadow_stride); if (j < ns) break; j -= ns; light++; }
                         size_t e = (size_t)light * W.shadow_stride + j;
                         o4 = W.shadow_o[e];
-                        dist_sq = W.rad[e].w; kind = dist_sq < 0.0f ? 1 : 2; out_idx = (uint32_t)e;
+                        kind = (W.rad[e].w < 0.0f ? 1 : 2) | (int)(light << 2); out_idx = (uint32_t)e;
                         if (W.shadow_dir) d4 = W.shadow_dir[e];
                         else {
                             const DevLight &Lt = S.lights[light];
@@ -379,17 +379,18 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                         }
                     }
                 }
-                if (kind == 1 && best.tri >= 0) cur = RT_DONE;                     // occlusion only needs TraceRay's bool (raytracer.cpp:385)
+                if ((kind & 3) == 1 && best.tri >= 0) cur = RT_DONE;                     // occlusion only needs TraceRay's bool (raytracer.cpp:385)
                 else { cur = top; top = stack[--sp]; }
             }
             if (cur == RT_DONE) {
                 if (kind == 0) {
                     W.hits[out_idx] = best;
                 } else {
-                    bool lit = best.tri < 0 || (kind == 2 && best.t * best.t <= dist_sq);   // raytracer.cpp:385 / 395-396
+                    const float4 r = W.rad[out_idx];                                     // w: squared light distance (point light)
+                    const uint32_t light = (uint32_t)kind >> 2;
+                    bool lit = best.tri < 0 || ((kind & 3) == 2 && best.t * best.t <= r.w);   // raytracer.cpp:385 / 395-396
                     if (lit) {
                         uint32_t slot = __float_as_uint(W.shadow_o[out_idx].w);
-                        float4 r = W.rad[out_idx];
                         float4 *dst = light == 0 ? W.acc + slot : W.acc_extra + (size_t)(light - 1) * W.shadow_stride + slot;
                         float4 a = *dst;
                         a.x += r.x; a.y += r.y; a.z += r.z;
