@@ -53,9 +53,9 @@ def select_workload(key: str):
 
 
 ROOFLINE_NOTE = {
-    "config2": "achieved counts SURVEY 8(d)'s algorithmic bytes (776 B per ray); the 2.6 MB scene is L1/L2-resident, so the measured DRAM traffic per ray "
+    "config2": "achieved counts SURVEY 8(d)'s algorithmic bytes (776 B per ray); the 4 MB scene (1.1 MB nodes + 3 MB triangle records) is L1/L2-resident, so the measured DRAM traffic per ray "
                "(`traffic` / rays per launch) is far BELOW the algorithmic figure and frac can exceed 1: on this scene the kernel is bound by the ALU pipe "
-               "(ncu, profiles/: 64-72 % of ALU-pipe peak, 68-77 % issue slots busy, DRAM < 8 %)",
+               "(ncu, profiles/: 57-70 % of ALU-pipe peak, 64-79 % issue slots busy, DRAM < 8 %)",
     "config3": "achieved counts SURVEY 8(d)'s algorithmic bytes (904 B per ray); ncu: the kernel waits on scattered node / triangle loads (L1 hit 60-70 %)",
     "config5": "achieved counts SURVEY 8(d)'s algorithmic bytes (904 B per ray); ncu: the kernel waits on scattered node / triangle loads (L1 hit 60-70 %)",
     "config4": "achieved counts SURVEY 8(d)'s algorithmic bytes (1032 B per ray); ncu (profiles/): 45-50 % of stall samples wait on node and triangle "
@@ -358,7 +358,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "spp_per_gpu": SPP if mode == "samples" else SPP / world,
                        "spp_total": total_spp, "partition": mode if world > 1 else "none",
                        "combine": "NCCL reduce(SUM) of 33 MB float4 frames inside the timed region" if world > 1 else "none",
-                       "l2": "256 MB memset flushes L2 before every step; per-step path-state streams (tens of GB) exceed the 126 MB L2" + ("; the 2.6 MB scene (nodes + triangle records) is L2-resident by design" if WORKLOAD_KEY == "config2" else "; the scene itself exceeds L2"),
+                       "l2": "256 MB memset flushes L2 before every step; per-step path-state streams (tens of GB) exceed the 126 MB L2" + ("; the 4 MB scene (nodes + triangle records) is L2-resident by design" if WORKLOAD_KEY == "config2" else "; the scene itself exceeds L2"),
                        "triangles": n_tris, "hierarchy_nodes": info["nodes"], "scene_create_s": scene_create_s,
                        "rays_per_step": rays // args.steps // 1, "waves_per_step": waves // args.steps,
                        "kernel_ms_per_step": {"k_trace_wave": trace_ms / args.steps, "k_logic": logic_ms / args.steps}},
