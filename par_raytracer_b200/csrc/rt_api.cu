@@ -229,7 +229,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     for (int attempt = 0; attempt < 2; ++attempt) {
         // attempt 1: strict (2k, 2k+1) pairing -> balanced tree of depth ceil(log2 n); mode 2 = surface-area search cost (default; RT_B200_PLOC_COST=diagonal: the squared-diagonal cost)
         const char *pc = getenv("RT_B200_PLOC_COST");
-        const int pair_mode = attempt ? 1 : ((pc && strcmp(pc, "diagonal") == 0) ? 0 : 2);
+        const int pair_mode = (attempt || (pc && strcmp(pc, "pairs") == 0)) ? 1 : ((pc && strcmp(pc, "diagonal") == 0) ? 0 : 2);
         k_ploc_init<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_sphere, tri_lo, tri_hi, tri_nrm0, tri_slab, cn[0], t); CKLB("k_ploc_init");
         uint32_t m = n, created = 0;
         int cur = 0;
