@@ -297,6 +297,12 @@ int rt_get_sample_counts(rt_scene *scene, uint32_t *out_host, uint32_t n);
  * [4]=bytes of node array, [5]=bytes of triangle records, [6]=build microseconds, [7]=reserved */
 int rt_get_hierarchy_info(const rt_scene *scene, uint64_t out[8]);
 
+/* Host-only (no device needed): the 15-bit quantisation grid rt_scene_create lays over scene bounds [lo, hi] for the default child
+ * bound of the GPU hierarchy (no reference counterpart: the reference's BoundingSphere nodes, bsphere.cpp:316-320, are floats).
+ * Plane q in [0, 32767] of axis a sits at mid[a] + (32768 + q) * step[a]. Returns RT_OK and *ok = 1 when the grid covers the bounds,
+ * *ok = 0 when no grid can (non-finite bounds: the scene then uses float boxes). Test hook for the placement's edge cases. */
+int rt_quant_grid(const float lo[3], const float hi[3], float step[3], float mid[3], int *ok);
+
 /* Random_Seed + n x Random_Next on the device (random.h:9-42); KAT hook for the parity tests. */
 int rt_rng_kat(int device, uint64_t seed, uint32_t n, uint64_t *out_host);
 

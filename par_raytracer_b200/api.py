@@ -29,7 +29,7 @@ RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
            "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat",
            "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap", "rt_build_group_hierarchy",
-           "rt_calculate_tangents", "rt_height_to_normal_map"]
+           "rt_calculate_tangents", "rt_height_to_normal_map", "rt_quant_grid"]
 
 
 class RtError(RuntimeError):

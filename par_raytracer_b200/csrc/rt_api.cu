@@ -171,6 +171,35 @@ static void host_phong_dirs(const std::vector<float> &spec_intensity, uint32_t s
 }
 
 // ---------------------------------------------------------------------------------------------
+// quantisation grid of QNode (host): 32764 steps across [lo, hi] per axis, at least one step of margin below lo.
+// The kernel decodes plane q as mid + (32768 + q) * step from these two FLOATS, so the grid is built from exactly them.
+// A scene far from the origin relative to its size rounds `mid` coarsely: the step is widened until the grid covers [lo, hi].
+// Returns false when no grid can (non-finite bounds).
+// ---------------------------------------------------------------------------------------------
+static bool place_quant_grid(double lo, double hi, float *step_out, float *mid_out, double *base_out) {
+    float step = (float)std::max((hi - lo) / 32764.0, 1e-30);
+    if (!(step > 0.0f)) step = 1e-30f;
+    float mid = 0.0f; double base = 0.0;
+    bool ok = false;
+    for (int it = 0; it < 200 && !ok; ++it) {
+        mid = (float)(lo - (double)step - 32768.0 * (double)step);
+        base = (double)mid + 32768.0 * (double)step;
+        ok = base <= lo && base + 32767.0 * (double)step >= hi;
+        if (!ok) step *= 1.25f;
+    }
+    *step_out = step; *mid_out = mid; *base_out = base;
+    return ok;
+}
+
+extern "C" int rt_quant_grid(const float lo[3], const float hi[3], float step[3], float mid[3], int *ok) {
+    g_err.clear();
+    if (!lo || !hi || !step || !mid || !ok) return fail(RT_ERR_ARG, "null argument");
+    *ok = 1;
+    for (int a = 0; a < 3; ++a) { double b; if (!place_quant_grid(lo[a], hi[a], &step[a], &mid[a], &b)) *ok = 0; }
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // hierarchy build orchestration (kernels in rt_build.cuh)
 // ---------------------------------------------------------------------------------------------
 static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInput &gin, bool has_tangents) {
@@ -274,20 +303,8 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         CKB(cudaStreamSynchronize(st));
         const float lo3[3] = {rlo.x, rlo.y, rlo.z}, hi3[3] = {rhi.x, rhi.y, rhi.z};
         for (int a = 0; a < 3; ++a) {
-            const double lo = lo3[a], hi = hi3[a];
-            float step = (float)std::max((hi - lo) / 32764.0, 1e-30);
-            if (!(step > 0.0f)) step = 1e-30f;
-            // The kernel decodes plane q as qmid + (32768 + q) * qstep from these two FLOATS, so the grid is built from exactly them.
-            // A scene far from the origin relative to its size rounds qmid coarsely: widen the step until the grid covers [lo, hi].
-            for (int it = 0; it < 200; ++it) {
-                const float mid = (float)(lo - (double)step - 32768.0 * (double)step);
-                qs[a] = (double)step;
-                qb[a] = (double)mid + 32768.0 * qs[a];
-                sc->d.qstep[a] = step; sc->d.qmid[a] = mid;
-                if (qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi) break;
-                step *= 1.25f;
-            }
-            if (!(qb[a] <= lo && qb[a] + 32767.0 * qs[a] >= hi)) grid_ok = false;     // non-finite extents: no grid can cover them
+            if (!place_quant_grid(lo3[a], hi3[a], &sc->d.qstep[a], &sc->d.qmid[a], &qb[a])) grid_ok = false;     // non-finite extents
+            qs[a] = (double)sc->d.qstep[a];
         }
     }
     if (!grid_ok && sc->bounds == RT_BOUNDS_QBOX) sc->bounds = RT_BOUNDS_BOX;   // float boxes need no grid (inf / NaN vertices behave as they do there)

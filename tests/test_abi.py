@@ -74,3 +74,40 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("the oracle harness", "").replace("Oracle", "").lower() or f in ("scenes.py", "types.py"), \
                     f"{f} mentions the oracle"
+
+
+def test_quantisation_grid_placement(lib):
+    """rt_quant_grid is host code: the 15-bit grid of the default node format must cover the scene bounds for any finite
+    bounds -- tiny, huge, degenerate (zero extent) and far from the origin, where `mid` rounds coarser than the ideal step --
+    with the planes the kernel will decode from the two floats per axis; non-finite bounds must be refused (ok = 0)."""
+    import ctypes as C
+    f3 = C.c_float * 3
+
+    def grid(lo, hi):
+        step, mid, ok = f3(), f3(), C.c_int(-1)
+        assert lib.rt_quant_grid(f3(*lo), f3(*hi), step, mid, C.byref(ok)) == 0
+        return np.array(step[:], np.float32), np.array(mid[:], np.float32), ok.value
+
+    rng = np.random.default_rng(7)
+    cases = [((-1, -1, -1), (1, 1, 1)), ((0, 0, 0), (0, 0, 0)), ((5, 5, 5), (5, 6, 5)), ((-1e-30, 0, 0), (1e-30, 1e-38, 0)),
+             ((-3e37, -1, 0), (3e37, 1, 1e-20)), ((1e7, -1e7, 3e6), (1e7 + 1, -1e7 + 2, 3e6 + 0.5)), ((16777216, 0, 0), (16777218, 1, 1))]
+    for _ in range(2000):
+        c = rng.normal(size=3) * 10.0 ** rng.uniform(-3, 8)
+        e = np.abs(rng.normal(size=3)) * 10.0 ** rng.uniform(-6, 6, size=3)
+        cases.append((tuple(np.float32(c - e)), tuple(np.float32(c + e))))
+    for lo, hi in cases:
+        lo32, hi32 = np.array(lo, np.float32), np.array(hi, np.float32)
+        if not np.all(np.isfinite(lo32) & np.isfinite(hi32)):
+            continue
+        step, mid, ok = grid(lo32, hi32)
+        assert ok == 1, (lo, hi)
+        assert np.all(step > 0) and np.all(np.isfinite(step)) and np.all(np.isfinite(mid))
+        base = mid.astype(np.float64) + 32768.0 * step.astype(np.float64)            # plane 0, exactly as the build computes it
+        top = base + 32767.0 * step.astype(np.float64)                                # plane 32767
+        assert np.all(base <= lo32.astype(np.float64)) and np.all(top >= hi32.astype(np.float64)), (lo, hi, step, mid)
+        ext = hi32.astype(np.float64) - lo32.astype(np.float64)
+        near = np.abs(lo32.astype(np.float64)) < 10.0 * np.maximum(ext, 1e-30)        # not far from the origin (float ulp of `mid` << step): the grid must be tight
+        assert np.all(step.astype(np.float64)[near] <= np.maximum(ext[near] / 32764.0, 1e-30) * 1.0001)
+    for lo, hi in [((0, 0, 0), (np.inf, 1, 1)), ((np.nan, 0, 0), (1, 1, 1)), ((-np.inf, 0, 0), (np.inf, 1, 1))]:
+        assert grid(lo, hi)[2] == 0
+    assert lib.rt_quant_grid(None, None, None, None, None) != 0
