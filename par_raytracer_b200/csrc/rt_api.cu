@@ -80,6 +80,7 @@ struct Pool {                 // per-render working set, kept between calls and 
     PathPool paths{};
     RayQueue q[2]{};
     HitRec *hits = nullptr;
+    uint32_t *ray_cnt = nullptr;       // per-path ray counts (PathPool::ray_cnt points here during the adaptive loop)
     ShadowQueue shadow{};
     uint32_t *counts = nullptr;        // [0],[1]: ray queue sizes (ping-pong), [2 + l]: shadow queue size of light l
     float4 *acc_extra = nullptr;       // per-path accumulators of lights >= 1
@@ -564,6 +565,8 @@ static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
     CK(p.mem.alloc(&p.paths.rng_cx, c)); CK(p.mem.alloc(&p.paths.rng_seed, c));
     CK(p.mem.alloc(&p.paths.acc, c)); CK(p.mem.alloc(&p.paths.node_T, c));
     CK(p.mem.alloc(&p.paths.frames, c * RT_FRAME_F4 * depth));
+    CK(p.mem.alloc(&p.ray_cnt, c));
+    p.paths.ray_cnt = nullptr;           // switched on only by the adaptive loop
     p.paths.capacity = capacity;
     for (int k = 0; k < 2; ++k) { CK(p.mem.alloc(&p.q[k].o, c)); CK(p.mem.alloc(&p.q[k].d, c)); }
     CK(p.mem.alloc(&p.hits, c));
@@ -801,7 +804,10 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
     const uint32_t limit = pool_limit();
     const uint32_t spp_chunk = std::min(sample_count, limit);
     const uint32_t pix_per_batch = std::max(1u, std::min(pixel_count, limit / spp_chunk));
-    rc = ensure_pool(sc, (uint32_t)std::min<uint64_t>((uint64_t)pix_per_batch * spp_chunk, (uint64_t)limit), params->bounce_depth);
+    uint64_t pool_want = (uint64_t)pix_per_batch * spp_chunk;
+    if ((flags & RT_FLAG_ADAPTIVE) && params->min_samples < params->max_samples)      // room for the second loop's chunks of up to 32 samples per pixel
+        pool_want = std::max<uint64_t>(pool_want, (uint64_t)pixel_count * std::min(32u, params->max_samples - params->min_samples));
+    rc = ensure_pool(sc, (uint32_t)std::min<uint64_t>(pool_want, (uint64_t)limit), params->bounce_depth);
     if (rc) return rc;
     Pool &p = sc->pool;
 
@@ -826,11 +832,13 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
 
     const bool adaptive = (flags & RT_FLAG_ADAPTIVE) && params->min_samples < params->max_samples;
     const uint32_t max_s = params->max_samples;
+    bool adaptive_counts = false;                     // ray_count = first pass + the rays of the ACCEPTED samples of the second loop
+    unsigned long long adaptive_first_pass_rays = 0, adaptive_accepted_rays = 0;
     uint32_t *d_nsamples = nullptr;
     if (adaptive) {
         rc = grow(sc, &sc->scratch, &sc->scratch_cap, (size_t)pixel_count * max_s);
         if (rc) return done(rc);
-        rc = grow(sc, &sc->ad_u32, &sc->ad_u32_cap, 5 * (size_t)pixel_count + 4);
+        rc = grow(sc, &sc->ad_u32, &sc->ad_u32_cap, 5 * (size_t)pixel_count + 8);
         if (rc) return done(rc);
         d_nsamples = sc->ad_u32;
     }
@@ -852,33 +860,49 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
         }
     }
     if (adaptive) {
-        // RenderPixel's second loop (main.cpp:246-258): one more sample per still-active pixel per iteration, jitter x 1.0
+        // RenderPixel's second loop (main.cpp:246-258), jitter x 1.0. The reference takes one more sample per pixel and iteration; here every
+        // still-active pixel gets its next K samples at once (K = 2, 4, 8, ...: at most twice what the pixel ends up using) and
+        // k_adaptive_update replays the reference's per-sample decisions over them. Samples past a pixel's stopping point are discarded,
+        // rays included (per-path ray counts), so colours, sample counts and ray_count are those of the one-at-a-time loop.
         uint32_t *lists[2][2] = {{sc->ad_u32 + pixel_count, sc->ad_u32 + 2 * (size_t)pixel_count},
                                  {sc->ad_u32 + 3 * (size_t)pixel_count, sc->ad_u32 + 4 * (size_t)pixel_count}};
         uint32_t *d_count = sc->ad_u32 + 5 * (size_t)pixel_count;
+        unsigned long long *d_rays = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(d_count + 1) + 7u) & ~(uintptr_t)7u);
+        CKR(cudaMemsetAsync(d_rays, 0, 8, st));
         k_adaptive_init<<<cdiv(pixel_count, 256), 256, 0, st>>>(pixel_count, d_ids, pixel_begin, lists[0][0], lists[0][1], d_nsamples, max_s);
         launches++;
+        adaptive_first_pass_rays = sc->stats.closest_rays + sc->stats.shadow_rays;
+        p.paths.ray_cnt = p.ray_cnt;
         uint32_t n_active = pixel_count;
         int cur = 0;
-        for (uint32_t samp = params->min_samples; samp < max_s && n_active > 0; ++samp) {
+        uint32_t K = 2;
+        for (uint32_t samp = params->min_samples; samp < max_s && n_active > 0;) {
+            const uint32_t Kc = std::max(1u, std::min(std::min(K, max_s - samp), p.capacity / std::max(1u, std::min(n_active, p.capacity))));
+            const uint32_t na_max = std::max(1u, p.capacity / Kc);
             CKR(cudaMemsetAsync(d_count, 0, 4, st));
-            for (uint32_t a0 = 0; a0 < n_active; a0 += p.capacity) {   // more active pixels than pool slots: chunks
-                const uint32_t na = std::min(p.capacity, n_active - a0);
+            for (uint32_t a0 = 0; a0 < n_active; a0 += na_max) {   // more active samples than pool slots: chunks
+                const uint32_t na = std::min(na_max, n_active - a0);
                 PrimaryGen gen;
                 memset(&gen, 0, sizeof(gen));
-                gen.cam = dcam; gen.base_seed = prm.base_seed; gen.pixel_ids = lists[cur][0] + a0; gen.n_slots = na; gen.spp = 1; gen.width = width;
+                gen.cam = dcam; gen.base_seed = prm.base_seed; gen.pixel_ids = lists[cur][0] + a0; gen.n_slots = na * Kc; gen.spp = Kc; gen.width = width;
                 gen.pixel_begin = 0; gen.pixel_local0 = 0; gen.sample_begin = sample_begin + samp; gen.jitter_scale = 1.0f; gen.enabled = 1;
-                rc = run_waves(sc, prm, na, flags, &launches, &gen);
-                if (rc) return done(rc);
-                k_adaptive_update<<<cdiv(na, 128), 128, 0, st>>>(p.paths.acc, na, samp, max_s, lists[cur][0] + a0, lists[cur][1] + a0, accum, sc->scratch,
-                                                                d_nsamples, lists[cur ^ 1][0], lists[cur ^ 1][1], d_count);
-                { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_adaptive_update failed: %s", cudaGetErrorString(e_))); }
+                rc = run_waves(sc, prm, na * Kc, flags, &launches, &gen);
+                if (rc) { p.paths.ray_cnt = nullptr; return done(rc); }
+                k_adaptive_update<<<cdiv(na, 128), 128, 0, st>>>(p.paths.acc, p.ray_cnt, na, samp, Kc, max_s, lists[cur][0] + a0, lists[cur][1] + a0, accum, sc->scratch,
+                                                                d_nsamples, lists[cur ^ 1][0], lists[cur ^ 1][1], d_count, d_rays);
+                { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { p.paths.ray_cnt = nullptr; return done(fail(RT_ERR_CUDA, "launch of k_adaptive_update failed: %s", cudaGetErrorString(e_))); } }
                 launches++;
             }
             CKR(cudaMemcpyAsync(&n_active, d_count, 4, cudaMemcpyDeviceToHost, st));
             CKR(cudaStreamSynchronize(st));
             cur ^= 1;
+            samp += Kc;
+            K = std::min(K * 2u, 1u << 20);
         }
+        p.paths.ray_cnt = nullptr;
+        CKR(cudaMemcpyAsync(&adaptive_accepted_rays, d_rays, 8, cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        adaptive_counts = true;
         sc->last_adaptive_pixels = pixel_count;
     }
     k_finalize<<<cdiv(pixel_count, 128), 128, 0, st>>>(accum, pixel_count, sample_count, d_nsamples, flags & 3u, (float4 *)out_dev, d_ids, pixel_begin);
@@ -894,7 +918,7 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
     sc->stats.kernel_launches = launches;
     { int rc_ = collect_wave_times(sc); if (rc_) return done(rc_); }
     if (out_counters) {
-        out_counters->ray_count = sc->stats.closest_rays + sc->stats.shadow_rays;
+        out_counters->ray_count = adaptive_counts ? adaptive_first_pass_rays + adaptive_accepted_rays : sc->stats.closest_rays + sc->stats.shadow_rays;
         out_counters->sphere_check_count = tc.sphere_checks;
         out_counters->mesh_check_count = tc.cluster_checks;
     }

@@ -31,6 +31,7 @@ struct PathPool {
     float4 *acc;                 // xyz: radiance gathered by the sample so far
     float4 *node_T;              // xyz: throughput of the in-flight node, w: iters | frames << 8 | draws << 16
     float4 *frames;              // [(level * RT_FRAME_F4 + k) * capacity + slot]
+    uint32_t *ray_cnt;           // NULL, or per path: TraceRay calls of this sample so far (adaptive sampling keeps the counts of discarded samples out of ray_count)
     uint32_t capacity;
 };
 
@@ -381,6 +382,11 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
     uint32_t pos = warp_push(n_out, emit);
     if (active) {
         P.acc[slot] = mk4(acc, 0.0f);
+        if (P.ray_cnt) {                               // rays this sample has asked for: its primary ray, every emitted ray, one shadow ray per light and shade
+            const uint32_t add = (emit ? 1u : 0u) + (shade_hit ? S.n_lights : 0u);
+            if (G.enabled) P.ray_cnt[slot] = 1u + add;
+            else if (add) P.ray_cnt[slot] += add;
+        }
         if (emit) {                                    // a finished path only leaves its radiance behind
             P.rng_cx[slot] = rng_pack(rng);
             P.node_T[slot] = mk4u(e_T, pack_state(e_iters, sp, rng.n));
@@ -458,29 +464,40 @@ __global__ void k_adaptive_init(uint32_t n_pixels, const uint32_t *pixel_ids, ui
     nsamples[p] = max_samples;
 }
 
-// One iteration of the loop at main.cpp:246-258 for every still-active pixel: the new sample (index samp) is stored and
-// added, the variance of the samples BEFORE it decides (main.cpp:253 -- the newest sample is excluded), and a converged
-// pixel divides by samp although samp + 1 samples were summed (main.cpp:262).
-__global__ void k_adaptive_update(const float4 *acc, uint32_t n_active, uint32_t samp, uint32_t max_samples, const uint32_t *act_pixel,
-                                  const uint32_t *act_local, float4 *accum, float4 *scratch, uint32_t *nsamples, uint32_t *out_pixel,
-                                  uint32_t *out_local, uint32_t *n_out) {
+// K consecutive iterations of the loop at main.cpp:246-258 for every still-active pixel, from K speculatively rendered samples
+// (indices samp0 .. samp0 + K - 1; slot i * K + k holds sample samp0 + k of active pixel i). Per sample, in order, exactly the
+// reference's step: the new sample is stored and added, the variance of the samples BEFORE it decides (main.cpp:253 -- the newest
+// sample is excluded), and a converged pixel divides by samp although samp + 1 samples were summed (main.cpp:262).
+// Samples after the stopping one were rendered for nothing: they touch neither the colour nor rays_out. Rendering them K at a time
+// is what makes the waves K times larger and the launch count K times smaller than one sample per iteration.
+__global__ void k_adaptive_update(const float4 *acc, const uint32_t *ray_cnt, uint32_t n_active, uint32_t samp0, uint32_t K, uint32_t max_samples,
+                                  const uint32_t *act_pixel, const uint32_t *act_local, float4 *accum, float4 *scratch, uint32_t *nsamples,
+                                  uint32_t *out_pixel, uint32_t *out_local, uint32_t *n_out, unsigned long long *rays_out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n_active;
     bool keep = false;
     uint32_t pl = 0, px = 0;
+    unsigned long long rays = 0;
     if (active) {
         pl = act_local[i]; px = act_pixel[i];
-        float4 a = acc[i];
         float4 *sc = scratch + (size_t)pl * max_samples;
-        sc[samp] = a;
         float4 c = accum[pl];
-        c.x += a.x; c.y += a.y; c.z += a.z;
-        accum[pl] = c;
-        float var = calc_variance(sc, samp);
         const float variance_threshold = 0.01f;
-        if (var <= variance_threshold) nsamples[pl] = samp;
-        else if (samp + 1u < max_samples) keep = true;
+        keep = true;
+        for (uint32_t k = 0; k < K && keep; ++k) {
+            const uint32_t samp = samp0 + k;
+            float4 a = acc[(size_t)i * K + k];
+            rays += ray_cnt[(size_t)i * K + k];
+            sc[samp] = a;
+            c.x += a.x; c.y += a.y; c.z += a.z;
+            float var = calc_variance(sc, samp);
+            if (var <= variance_threshold) { nsamples[pl] = samp; keep = false; }
+            else if (!(samp + 1u < max_samples)) keep = false;
+        }
+        accum[pl] = c;
     }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, o);
+    if ((threadIdx.x & 31u) == 0 && rays) atomicAdd(rays_out, rays);
     uint32_t pos = warp_push(n_out, keep);
     if (keep) { out_pixel[pos] = px; out_local[pos] = pl; }
 }
