@@ -284,6 +284,43 @@ def test_adaptive_sampling_against_reference(gscene):
     assert np.array_equal(ns, ns2) and np.array_equal(bits(img), bits(img2))
 
 
+def test_adaptive_chunking_is_invisible(monkeypatch):
+    """The second loop renders the next 2, 4, 8 ... samples of every active pixel speculatively and replays the reference's per-sample
+    decisions. Whatever the chunking (default pool: full chunks; a pool smaller than the active-pixel list: one sample at a time, in
+    sub-batches), image bits, per-pixel sample counts and ray_count must be identical -- and equal to the oracle's one-at-a-time loop.
+    The scene is dimmed so that many pixels sit near the 0.01 variance threshold and stop at many different sample counts."""
+    import dataclasses
+    base = scenes.spheres_plane_scene(grid=2, nu=16, nv=8, textured=True)
+    L = base.lights.copy(); L["color"] *= 0.15
+    sd = dataclasses.replace(base, lights=L)
+    W, H = 96, 64
+    h = base.camera_hint
+    cam = types.make_camera(h["fov"], W, H, h["position"], h["facing"])
+    p = types.default_params(spp=4); p["min_samples"], p["max_samples"] = 4, 30        # chunks 2, 4, 8, 12 after the 4-sample first pass
+    p["background_color"] = p["background_color"] * np.float32(0.15)
+    O = oracle.OracleScene(sd)
+    ref, ns_o, cnt_o, _ = O.render(cam, p, W, H, threads=8)
+    assert len(np.unique(ns_o)) >= 8 and ns_o.min() == 4 and ns_o.max() == 30           # stops at many different counts
+    S = api.Scene(sd)
+    a, ca = S.render_task(cam, p, W, H, flags=api.RT_FLAG_ADAPTIVE)
+    na = S.sample_counts(W * H)
+    same = na == ns_o
+    assert same.mean() >= 0.995, f"sample counts differ on {(~same).sum()} pixels"     # colours agree to ~1e-7: threshold ties may flip
+    assert np.allclose(a[same], ref[same], rtol=RTOL, atol=ATOL)
+    if same.all():
+        assert ca["ray_count"] == cnt_o["ray_count"]
+    for pool in ("1000", "9001"):                                              # fewer slots than pixels; fewer than pixels x chunk
+        monkeypatch.setenv("RT_B200_POOL", pool)
+        S2 = api.Scene(sd)                                                    # a fresh pool: it never shrinks on an existing scene
+        b, cb = S2.render_task(cam, p, W, H, flags=api.RT_FLAG_ADAPTIVE)
+        nb = S2.sample_counts(W * H)
+        S2.close()
+        assert np.array_equal(na, nb)
+        assert np.array_equal(bits(a), bits(b)) and ca["ray_count"] == cb["ray_count"]
+    monkeypatch.delenv("RT_B200_POOL")
+    S.close()
+
+
 def test_tonemap_on_device(gscene):
     """GPU tone map + RGBA8 pack vs the PNG the reference wrote for the same float frame. The reference sums logf in 32-bit
     scan order; the GPU reduces in double, and logf/expf are CUDA's: scene_luma within 2e-6 relative, and because the pack
