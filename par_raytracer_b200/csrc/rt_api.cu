@@ -853,7 +853,7 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
             gen.pixel_begin = pixel_begin; gen.pixel_local0 = p0; gen.sample_begin = sample_begin + s0; gen.jitter_scale = 0.5f; gen.enabled = 1;
             rc = run_waves(sc, prm, n_slots, flags, &launches, &gen);
             if (rc) return done(rc);
-            if (adaptive) k_resolve_scratch<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, sc->scratch, max_s, p0, s0);
+            if (adaptive) k_resolve_scratch<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, sc->scratch, pixel_count, p0, s0);
             else k_resolve<<<cdiv(npix, 128), 128, 0, st>>>(p.paths.acc, npix, ns, accum, p0);
             { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return done(fail(RT_ERR_CUDA, "launch of k_resolve failed: %s", cudaGetErrorString(e_))); }
             launches++;
@@ -888,7 +888,7 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
                 gen.pixel_begin = 0; gen.pixel_local0 = 0; gen.sample_begin = sample_begin + samp; gen.jitter_scale = 1.0f; gen.enabled = 1;
                 rc = run_waves(sc, prm, na * Kc, flags, &launches, &gen);
                 if (rc) { p.paths.ray_cnt = nullptr; return done(rc); }
-                k_adaptive_update<<<cdiv(na, 128), 128, 0, st>>>(p.paths.acc, p.ray_cnt, na, samp, Kc, max_s, lists[cur][0] + a0, lists[cur][1] + a0, accum, sc->scratch,
+                k_adaptive_update<<<cdiv(na, 128), 128, 0, st>>>(p.paths.acc, p.ray_cnt, na, samp, Kc, max_s, lists[cur][0] + a0, lists[cur][1] + a0, accum, sc->scratch, (size_t)pixel_count,
                                                                 d_nsamples, lists[cur ^ 1][0], lists[cur ^ 1][1], d_count, d_rays);
                 { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { p.paths.ray_cnt = nullptr; return done(fail(RT_ERR_CUDA, "launch of k_adaptive_update failed: %s", cudaGetErrorString(e_))); } }
                 launches++;

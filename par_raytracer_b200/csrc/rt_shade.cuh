@@ -424,8 +424,9 @@ __global__ void k_finalize(const float4 *accum, uint32_t n_pixels, uint32_t n_sa
 }
 
 // ---- adaptive sampling: RenderPixel's second loop (main.cpp:245-258) ----------------------------------------
-// Phase A keeps every sample colour of the min_samples pass (the reference's scratch_buffer, main.cpp:232, 241).
-__global__ void k_resolve_scratch(const float4 *acc, uint32_t n_pixels, uint32_t spp, float4 *accum, float4 *scratch, uint32_t max_samples,
+// Phase A keeps every sample colour of the min_samples pass (the reference's scratch_buffer, main.cpp:232, 241), sample-major:
+// scratch[sample * stride + pixel], so that neighbouring pixels' re-reads in k_adaptive_update coalesce.
+__global__ void k_resolve_scratch(const float4 *acc, uint32_t n_pixels, uint32_t spp, float4 *accum, float4 *scratch, uint32_t stride,
                                   uint32_t pixel_local0, uint32_t samp0) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pixels) return;
@@ -433,21 +434,21 @@ __global__ void k_resolve_scratch(const float4 *acc, uint32_t n_pixels, uint32_t
     float4 c = accum[pl];
     for (uint32_t s = 0; s < spp; ++s) {
         float4 a = acc[(size_t)p * spp + s];
-        scratch[(size_t)pl * max_samples + samp0 + s] = a;
+        scratch[(size_t)(samp0 + s) * stride + pl] = a;
         c.x += a.x; c.y += a.y; c.z += a.z;
     }
     accum[pl] = c;
 }
 
-// CalculateVariance + Color_Distance (main.cpp:179-186, 206-222) over the first `count` samples, same operation order
-RT_DEVICE float calc_variance(const float4 *vals, uint32_t count) {
-    float mx = 0.0f, my = 0.0f, mz = 0.0f;
-    for (uint32_t i = 0; i < count; ++i) { float4 v = vals[i]; mx += v.x; my += v.y; mz += v.z; }
+// CalculateVariance + Color_Distance (main.cpp:179-186, 206-222) over the first `count` samples of one pixel (vals[i * stride]), same
+// operation order. `sum` = the samples added left to right from 0.0f -- which is exactly what RenderPixel's running colour holds
+// before the newest sample is added, so the mean's first loop need not be re-run.
+RT_DEVICE float calc_variance(const float4 *vals, size_t stride, uint32_t count, float4 sum) {
     float fc = (float)count;
-    mx = mx / fc; my = my / fc; mz = mz / fc;
+    float mx = sum.x / fc, my = sum.y / fc, mz = sum.z / fc;
     float variance = 0.0f;
     for (uint32_t i = 0; i < count; ++i) {
-        float4 v = vals[i];
+        float4 v = vals[(size_t)i * stride];
         float d = fabsf(v.x - mx) + fabsf(v.y - my) + fabsf(v.z - mz);
         variance += d * d;
     }
@@ -471,7 +472,7 @@ __global__ void k_adaptive_init(uint32_t n_pixels, const uint32_t *pixel_ids, ui
 // Samples after the stopping one were rendered for nothing: they touch neither the colour nor rays_out. Rendering them K at a time
 // is what makes the waves K times larger and the launch count K times smaller than one sample per iteration.
 __global__ void k_adaptive_update(const float4 *acc, const uint32_t *ray_cnt, uint32_t n_active, uint32_t samp0, uint32_t K, uint32_t max_samples,
-                                  const uint32_t *act_pixel, const uint32_t *act_local, float4 *accum, float4 *scratch, uint32_t *nsamples,
+                                  const uint32_t *act_pixel, const uint32_t *act_local, float4 *accum, float4 *scratch, size_t stride, uint32_t *nsamples,
                                   uint32_t *out_pixel, uint32_t *out_local, uint32_t *n_out, unsigned long long *rays_out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = i < n_active;
@@ -480,7 +481,7 @@ __global__ void k_adaptive_update(const float4 *acc, const uint32_t *ray_cnt, ui
     unsigned long long rays = 0;
     if (active) {
         pl = act_local[i]; px = act_pixel[i];
-        float4 *sc = scratch + (size_t)pl * max_samples;
+        float4 *sc = scratch + pl;                          // sample s of this pixel: sc[s * stride]
         float4 c = accum[pl];
         const float variance_threshold = 0.01f;
         keep = true;
@@ -488,9 +489,9 @@ __global__ void k_adaptive_update(const float4 *acc, const uint32_t *ray_cnt, ui
             const uint32_t samp = samp0 + k;
             float4 a = acc[(size_t)i * K + k];
             rays += ray_cnt[(size_t)i * K + k];
-            sc[samp] = a;
+            float var = calc_variance(sc, stride, samp, c);     // c: the samples before the newest, summed in order (main.cpp:242, 251)
+            sc[(size_t)samp * stride] = a;
             c.x += a.x; c.y += a.y; c.z += a.z;
-            float var = calc_variance(sc, samp);
             if (var <= variance_threshold) { nsamples[pl] = samp; keep = false; }
             else if (!(samp + 1u < max_samples)) keep = false;
         }
