@@ -170,9 +170,13 @@ def cpu_arm(scene_data, cam, params, budget_s: float, steps: int = 1, warmup: in
     chosen by a 1-spp pilot so that one step is about `budget_s` seconds. Returns a dict."""
     from oracle import oracle, ref_harness
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    xs = np.arange(12, WIDTH, 24, dtype=np.uint32)
-    ys = np.arange(12, HEIGHT, 24, dtype=np.uint32)
-    ids = (ys[:, None] * np.uint32(WIDTH) + xs[None, :]).reshape(-1).astype(np.uint32)
+
+    def subset(stride):
+        xs = np.arange(stride // 2, WIDTH, stride, dtype=np.uint32)
+        ys = np.arange(stride // 2, HEIGHT, stride, dtype=np.uint32)
+        return (ys[:, None] * np.uint32(WIDTH) + xs[None, :]).reshape(-1).astype(np.uint32)
+    stride = 24
+    ids = subset(stride)
     seed = int(params["base_seed"])
     if ref_harness.available():
         kind = "reference"
@@ -196,7 +200,14 @@ def cpu_arm(scene_data, cam, params, budget_s: float, steps: int = 1, warmup: in
             _, _, cnt, sec = O.render(cam, p, WIDTH, HEIGHT, pixel_ids=ids, threads=cores)
             return int(cnt["ray_count"]), sec
     rays1, sec1 = run(1)
+    # pilot: 1 spp on every 24th pixel. The sample is then grown -- first in spp (up to the workload's), then in pixels (every 12th, 8th,
+    # 6th, 4th) -- until one step is about `budget_s` seconds of work on this box's cores.
     spp = int(max(1, min(SPP, round(budget_s / max(sec1, 1e-6)))))
+    if spp == SPP:
+        for cand in (12, 8, 6, 4):
+            if sec1 * SPP * (24.0 / cand) ** 2 <= budget_s * 1.25:
+                stride = cand
+        ids = subset(stride)
     for _ in range(warmup):
         run(spp)
     tot_r, tot_s = 0, 0.0
@@ -204,7 +215,7 @@ def cpu_arm(scene_data, cam, params, budget_s: float, steps: int = 1, warmup: in
         r, s = run(spp)
         tot_r += r; tot_s += s
     return {"value": tot_r / tot_s / 1e6, "unit": "Mrays/s", "cores": cores, "kind": kind,
-            "sample": f"{len(ids)} pixels (every 24th in x and y of 1920x1080) x {spp} spp, {tot_r // max(1, steps)} rays/step, "
+            "sample": f"{len(ids)} pixels (every {stride}th in x and y of {WIDTH}x{HEIGHT}) x {spp} spp, {tot_r // max(1, steps)} rays/step, "
                       f"per-(pixel,sample) seeding, {cores} threads over contiguous pixel chunks",
             "seconds_per_step": tot_s / max(1, steps), "rays": tot_r}
 
