@@ -347,6 +347,81 @@ __global__ void k_ploc_merge(uint32_t m, uint32_t n, uint32_t nodes_created, con
     }
 }
 
+// ---- 3b. tree rotations ------------------------------------------------------------------------------
+// One bottom-up sweep of local restructuring (Kensler-style rotations): at every internal node N = {L, R}, swapping L with a
+// grandchild under R (or R with a grandchild under L) is applied when it shrinks the surface area of the child it rebuilds. Leaves walk
+// up; the second thread to arrive at a node processes it, so everything below N is final and nobody else touches it. Only the
+// rebuilt child changes bounds / size / kept; N's own bounds do not. Any tree is a valid hierarchy -- this only buys fewer node visits.
+RT_DEVICE float box_half_area(float4 lo, float4 hi) {
+    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+RT_DEVICE float union_half_area(float4 la, float4 ha, float4 lb, float4 hb) {
+    float dx = fmaxf(ha.x, hb.x) - fminf(la.x, lb.x), dy = fmaxf(ha.y, hb.y) - fminf(la.y, lb.y), dz = fmaxf(ha.z, hb.z) - fminf(la.z, lb.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+RT_DEVICE void temp_node_rebuild(TempTree &t, int32_t v) {          // bounds / size / kept / nsum of v from its two children
+    const int32_t a = t.c0[v], b = t.c1[v];
+    float4 la = t.lo[a], lb = t.lo[b], ha = t.hi[a], hb = t.hi[b];
+    t.lo[v] = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+    t.hi[v] = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+    const uint32_t sz = t.size[a] + t.size[b];
+    t.size[v] = sz;
+    t.kept[v] = sz > RT_LEAF_MAX ? 1u + t.kept[a] + t.kept[b] : 0u;
+    t.sphere[v] = enclose_spheres(t.sphere[a], t.sphere[b]);
+    float4 na = t.nsum[a], nb = t.nsum[b];
+    t.nsum[v] = make_float4(na.x + nb.x, na.y + nb.y, na.z + nb.z, FLT_MAX);
+    t.slab[v] = make_float4(0, 0, 0, -FLT_MAX);
+}
+__global__ void k_rotate(uint32_t n, TempTree t, uint32_t *visit, uint32_t *n_rotations) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t N = t.parent[i];
+    while (N >= 0) {
+        __threadfence();
+        if (atomicAdd(&visit[N], 1u) == 0u) return;                 // the sibling subtree is not finished: its thread will carry on
+        __threadfence();
+        const int32_t L = t.c0[N], R = t.c1[N];
+        const bool Li = L >= (int32_t)n, Ri = R >= (int32_t)n;       // internal temp nodes live at [n, 2n - 1)
+        float best = 0.0f; int which = 0;
+        const float4 Llo = t.lo[L], Lhi = t.hi[L], Rlo = t.lo[R], Rhi = t.hi[R];
+        if (Ri) {
+            const int32_t a = t.c0[R], b = t.c1[R];
+            const float now = box_half_area(Rlo, Rhi);
+            const float g1 = now - union_half_area(Llo, Lhi, t.lo[b], t.hi[b]);      // L <-> a : R becomes {L, b}
+            const float g2 = now - union_half_area(t.lo[a], t.hi[a], Llo, Lhi);      // L <-> b : R becomes {a, L}
+            if (g1 > best) { best = g1; which = 1; }
+            if (g2 > best) { best = g2; which = 2; }
+        }
+        if (Li) {
+            const int32_t c = t.c0[L], d = t.c1[L];
+            const float now = box_half_area(Llo, Lhi);
+            const float g3 = now - union_half_area(Rlo, Rhi, t.lo[d], t.hi[d]);      // R <-> c : L becomes {R, d}
+            const float g4 = now - union_half_area(t.lo[c], t.hi[c], Rlo, Rhi);      // R <-> d : L becomes {c, R}
+            if (g3 > best) { best = g3; which = 3; }
+            if (g4 > best) { best = g4; which = 4; }
+        }
+        if (which == 1 || which == 2) {
+            const int32_t x = which == 1 ? t.c0[R] : t.c1[R];
+            if (which == 1) t.c0[R] = L; else t.c1[R] = L;
+            t.c0[N] = x; t.parent[x] = N; t.parent[L] = R;
+            temp_node_rebuild(t, R);
+            atomicAdd(n_rotations, 1u);
+        } else if (which == 3 || which == 4) {
+            const int32_t x = which == 3 ? t.c0[L] : t.c1[L];
+            if (which == 3) t.c0[L] = R; else t.c1[L] = R;
+            t.c1[N] = x; t.parent[x] = N; t.parent[R] = L;
+            temp_node_rebuild(t, L);
+            atomicAdd(n_rotations, 1u);
+        }
+        {   // N keeps its bounds and size; its kept count follows its (possibly rebuilt) children
+            const uint32_t sz = t.size[N];
+            t.kept[N] = sz > RT_LEAF_MAX ? 1u + t.kept[t.c0[N]] + t.kept[t.c1[N]] : 0u;
+        }
+        N = t.parent[N];
+    }
+}
+
 // ---- 4. layout -------------------------------------------------------------------------------------
 
 // Per temp node: first triangle slot of its subtree in cluster order, pre-order index among kept nodes, depth.
