@@ -886,7 +886,9 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
         int cur = 0;
         uint32_t K = 2;
         for (uint32_t samp = params->min_samples; samp < max_s && n_active > 0;) {
-            const uint32_t Kc = std::max(1u, std::min(std::min(K, max_s - samp), p.capacity / std::max(1u, std::min(n_active, p.capacity))));
+            // chunk = the doubling schedule, or whatever it takes to put ~4 M samples in flight (a 720x480 frame cannot fill the chip with less)
+            const uint32_t K_fill = (uint32_t)std::min<uint64_t>(((4ull << 20) + n_active - 1) / n_active, 1u << 20);
+            const uint32_t Kc = std::max(1u, std::min(std::min(std::max(K, K_fill), max_s - samp), p.capacity / std::max(1u, std::min(n_active, p.capacity))));
             const uint32_t na_max = std::max(1u, p.capacity / Kc);
             CKR(cudaMemsetAsync(d_count, 0, 4, st));
             for (uint32_t a0 = 0; a0 < n_active; a0 += na_max) {   // more active samples than pool slots: chunks
