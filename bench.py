@@ -55,7 +55,7 @@ def select_workload(key: str):
 ROOFLINE_NOTE = {
     "config2": "achieved counts SURVEY 8(d)'s algorithmic bytes (776 B per ray); the 4 MB scene (1.1 MB nodes + 3 MB triangle records) is L1/L2-resident, so the measured DRAM traffic per ray "
                "(`traffic` / rays per launch) is far BELOW the algorithmic figure and frac can exceed 1: on this scene the kernel is bound by the ALU pipe "
-               "(ncu, profiles/: 57-70 % of ALU-pipe peak, 64-79 % issue slots busy, DRAM < 8 %)",
+               "(ncu, profiles/: 55-69 % of ALU-pipe peak, 63-80 % issue slots busy, DRAM < 9 %)",
     "config3": "achieved counts SURVEY 8(d)'s algorithmic bytes (904 B per ray); ncu: the kernel waits on scattered node / triangle loads (L1 hit 60-70 %)",
     "config5": "achieved counts SURVEY 8(d)'s algorithmic bytes (904 B per ray); ncu: the kernel waits on scattered node / triangle loads (L1 hit 60-70 %)",
     "config4": "achieved counts SURVEY 8(d)'s algorithmic bytes (1032 B per ray); ncu (profiles/): 45-50 % of stall samples wait on node and triangle "
