@@ -197,6 +197,10 @@ typedef struct rt_scene rt_scene;           /* opaque device-resident scene + GP
 int  rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene);
 void rt_scene_destroy(rt_scene *scene);
 
+/* Number of CUDA devices this process sees (0 if none / no driver): lets a host that does not link the CUDA runtime pick
+ * `device = rank % rt_device_count()`. */
+int  rt_device_count(void);
+
 /* Thread-local description of the last error on this thread ("" if none). */
 const char *rt_last_error(void);
 int  rt_abi_version(void);
@@ -215,14 +219,79 @@ int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params *params,
               float *out_rgba_host, rt_counters *out_counters);
 
 /* Same, output left in DEVICE memory (for the NCCL combine that replaces MPI_Gather,
- * main.cpp:345-347). `stream` is a cudaStream_t (NULL = the scene's own stream); the call
- * returns after enqueueing only when every wave could be scheduled without a host
- * read-back, otherwise it synchronises `stream` internally. pixel_ids is a HOST pointer. */
+ * main.cpp:345-347). `stream` is the caller's cudaStream_t; NULL (handle 0) means the LEGACY
+ * default stream. The render runs on the scene's own stream, ordered AFTER everything already
+ * enqueued on `stream` (the caller's memset of the frame, a previous combine reading it), and `stream`
+ * is made to wait for the result; the call itself returns after the scene's stream has drained
+ * (the counters are read back). pixel_ids is a HOST pointer. */
 int rt_render_device(rt_scene *scene, const rt_camera *cam, const rt_params *params,
                      uint32_t width, uint32_t height,
                      const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count,
                      uint32_t sample_begin, uint32_t sample_count, uint32_t flags,
                      float *out_rgba_device, void *stream, rt_counters *out_counters);
+
+/* ---- Render's partition + MPI_Gather (main.cpp:311-319, 345-347) on N GPUs ---------
+ *
+ * The reference shards contiguous pixel-index ranges over MPI ranks (scene replicated per rank) and gathers the
+ * ranges on rank 0. Here one "rank" is one GPU; the combine is an NCCL reduce over NVLink (or, inside one process,
+ * direct peer-memory stores / loads), followed on the root by the resolve it implies -- all inside the library:
+ *
+ *   RT_PART_TILES    interleaved tile x tile squares, round-robin over ranks (contiguous ranges load-balance badly:
+ *                    NOTES.txt:25). Ranks write disjoint pixels of zero-initialised frames, so the reduce(SUM) is
+ *                    bit-identical to the reference's MPI_Gather (x + 0 == x).
+ *   RT_PART_RANGES   the reference's own split: rank r renders [r * cpp, (r + 1) * cpp), cpp = ceil(W*H / ranks).
+ *   RT_PART_SAMPLES  every rank renders all pixels for a sample sub-range as raw sums; reduce(SUM), then / total
+ *                    samples, w = 1 (main.cpp:262-263). Not the reference's partition: toleranced (2e-6), not bit-exact.
+ */
+typedef struct rt_comm rt_comm;             /* one rank's handle on a group of GPUs (NCCL communicator + combine buffers) */
+
+#define RT_COMM_ID_BYTES 128
+#define RT_PART_TILES   0
+#define RT_PART_RANGES  1
+#define RT_PART_SAMPLES 2
+
+/* ncclGetUniqueId: called by ONE rank, which hands the bytes to the others through the host's own channel
+ * (the reference host has MPI: one MPI_Bcast; bench.py uses torch.distributed's store). */
+int rt_comm_unique_id(uint8_t out_id[RT_COMM_ID_BYTES]);
+/* ncclCommInitRank for `rank` of `n_ranks` on CUDA device `device`; collective over the ranks (one process or thread each). */
+int rt_comm_create(int n_ranks, int rank, const uint8_t id[RT_COMM_ID_BYTES], int device, rt_comm **out_comm);
+/* One process driving n GPUs: out_comms[i] is rank i on devices[i] (devices == NULL: 0 .. n-1). Peer access between the
+ * devices is enabled where the hardware allows it; rt_render_multi then gathers through peer memory and needs no NCCL. */
+int rt_comm_create_local(int n, const int *devices, rt_comm **out_comms);
+void rt_comm_destroy(rt_comm *comm);
+int rt_comm_rank(const rt_comm *comm);
+int rt_comm_size(const rt_comm *comm);
+
+/* Host-only (no device needed): the linear pixel ids of the tiles rank `rank` of `n_ranks` owns under RT_PART_TILES --
+ * tile t = ty * tiles_x + tx goes to rank t % n_ranks; inside a tile pixels are listed row by row. out_ids may be NULL
+ * (count only). *out_count receives the number of ids; out_ids must hold that many. */
+int rt_partition_tiles(uint32_t width, uint32_t height, uint32_t tile, int rank, int n_ranks, uint32_t *out_ids, uint32_t *out_count);
+
+/* This rank's share of Render() AND the combine, in one call (collective over the ranks of `comm`): partition
+ * (main.cpp:311-317 or the tile / sample form), render on `scene`'s GPU, ncclReduce of the float4 frames to `root` on the
+ * render stream, the resolve the partition implies (samples: / total, w = 1), and -- optionally, root only -- the tone map
+ * (rt_tonemap_device) and the download. Samples per pixel = params->min_samples (RT_FLAG_ADAPTIVE: min..max, pixel
+ * partitions only). flags: RT_FLAG_ADAPTIVE | RT_FLAG_TIME_KERNELS | RT_FLAG_COUNTERS.
+ *   out_rgba_host   root: W*H*4 floats (Framebuffer.pixels) or NULL (frame stays on the device, see rt_comm_frame)
+ *   out_rgba8_host  root: W*H*4 bytes after the reference's tone map, or NULL;  out_scene_luma: its LogAverageLuma
+ *   out_counters    root: counters summed over ranks; other ranks: their own */
+int rt_render_combined(rt_scene *scene, rt_comm *comm, const rt_camera *cam, const rt_params *params,
+                       uint32_t width, uint32_t height, int partition, uint32_t tile, uint32_t flags, int root,
+                       float *out_rgba_host, uint8_t *out_rgba8_host, float *out_scene_luma, rt_counters *out_counters);
+
+/* Render() on n GPUs of ONE process (what RenderB200 calls when a rank sees several GPUs): scenes[i] lives on the device of
+ * comms[i] (rt_comm_create_local). One host thread per GPU; with peer access the tiles are stored straight into the root GPU's
+ * frame over NVLink (no reduce, no zero-fill) and sample sums are added by ONE kernel on the root reading its peers' frames in
+ * rank order (deterministic); without peer access the ranks fall back to rt_render_combined's NCCL reduce. */
+int rt_render_multi(rt_scene *const *scenes, rt_comm *const *comms, int n, const rt_camera *cam, const rt_params *params,
+                    uint32_t width, uint32_t height, int partition, uint32_t tile, uint32_t flags,
+                    float *out_rgba_host, uint8_t *out_rgba8_host, float *out_scene_luma, rt_counters *out_counters);
+
+/* The combined W*H float4 frame of the last rt_render_combined / rt_render_multi on this rank (device pointer; meaningful on root). */
+const float *rt_comm_frame(const rt_comm *comm);
+/* out[0] = ms of zero-fill + reduce + resolve (CUDA events on the render stream), out[1] = ms of tone map + download,
+ * out[2] = bytes this rank contributed to the reduce, out[3] = 1 if the last combine went through peer memory, 0 = NCCL */
+int rt_comm_get_stats(const rt_comm *comm, double out[4]);
 
 /* ---- TraceRay (raytracer.cpp:159-232) ------------------------------------------- */
 

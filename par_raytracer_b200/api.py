@@ -29,7 +29,13 @@ RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",
            "rt_trace_rays", "rt_trace_primary", "rt_trace_color", "rt_get_stats", "rt_get_hierarchy_info", "rt_rng_kat",
            "rt_get_sample_counts", "rt_tonemap_device", "rt_tonemap", "rt_build_group_hierarchy",
-           "rt_calculate_tangents", "rt_height_to_normal_map", "rt_quant_grid"]
+           "rt_calculate_tangents", "rt_height_to_normal_map", "rt_quant_grid",
+           "rt_comm_unique_id", "rt_comm_create", "rt_comm_create_local", "rt_comm_destroy", "rt_comm_rank", "rt_comm_size",
+           "rt_partition_tiles", "rt_device_count", "rt_render_combined", "rt_render_multi", "rt_comm_frame", "rt_comm_get_stats"]
+
+RT_PART_TILES, RT_PART_RANGES, RT_PART_SAMPLES = 0, 1, 2
+PARTITIONS = {"tiles": RT_PART_TILES, "ranges": RT_PART_RANGES, "samples": RT_PART_SAMPLES}
+RT_COMM_ID_BYTES = 128
 
 
 class RtError(RuntimeError):
@@ -51,6 +57,15 @@ def load_library():
         L.rt_scene_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         L.rt_scene_destroy.argtypes = [C.c_void_p]
         L.rt_scene_destroy.restype = None
+        L.rt_comm_destroy.argtypes = [C.c_void_p]
+        L.rt_comm_destroy.restype = None
+        L.rt_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.rt_comm_create_local.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rt_comm_frame.argtypes = [C.c_void_p]
+        L.rt_comm_frame.restype = C.c_void_p
+        L.rt_comm_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.rt_comm_rank.argtypes = [C.c_void_p]
+        L.rt_comm_size.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -164,14 +179,16 @@ class Scene:
 
     # ---- Render / RenderTask ----------------------------------------------------------------
     def render_task(self, cam, params, width, height, pixel_begin=0, pixel_count=None, pixel_ids=None, sample_begin=0,
-                    sample_count=None, flags=RT_OUT_MEAN):
+                    sample_count=None, flags=RT_OUT_MEAN, out=None):
         cam = np.asarray(cam, CAMERA).reshape(1); params = np.asarray(params, PARAMS).reshape(1)
         ids = None if pixel_ids is None else np.ascontiguousarray(pixel_ids, np.uint32)
         if pixel_count is None:
             pixel_count = len(ids) if ids is not None else width * height - pixel_begin
         if sample_count is None:
             sample_count = int(params[0]["min_samples"])
-        out = np.zeros((pixel_count, 4), np.float32)
+        if out is None:
+            out = np.zeros((pixel_count, 4), np.float32)
+        assert out.dtype == np.float32 and out.size == pixel_count * 4 and out.flags["C_CONTIGUOUS"]
         cnt = np.zeros(1, COUNTERS)
         _check(self.lib.rt_render(self.h, _p(cam), _p(params), C.c_uint32(width), C.c_uint32(height), _p(ids),
                                   C.c_uint32(pixel_begin), C.c_uint32(pixel_count), C.c_uint32(sample_begin),
@@ -228,3 +245,110 @@ class Scene:
         _check(self.lib.rt_trace_color(self.h, _p(params), _p(rays), _p(seeds), C.c_uint64(len(rays)), _p(out), _p(cnt)),
                "rt_trace_color")
         return out, cnt[0]
+
+
+# ---- Render's partition + MPI_Gather on N GPUs (main.cpp:311-319, 345-347) -------------------------------------------
+def partition_tiles(width: int, height: int, rank: int, world: int, tile: int = 32) -> np.ndarray:
+    """rt_partition_tiles (host-only): linear pixel ids of the interleaved tiles `rank` owns."""
+    L = load_library()
+    n = C.c_uint32(0)
+    _check(L.rt_partition_tiles(C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile), C.c_int(rank), C.c_int(world), None, C.byref(n)),
+           "rt_partition_tiles")
+    ids = np.zeros(n.value, np.uint32)
+    _check(L.rt_partition_tiles(C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile), C.c_int(rank), C.c_int(world), _p(ids), C.byref(n)),
+           "rt_partition_tiles")
+    return ids
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (one rank calls it, the host distributes the 128 bytes)."""
+    buf = (C.c_uint8 * RT_COMM_ID_BYTES)()
+    _check(load_library().rt_comm_unique_id(buf), "rt_comm_unique_id")
+    return bytes(buf)
+
+
+class Comm:
+    """One rank's rt_comm: NCCL communicator (or peer-memory group member) + the combine buffers."""
+
+    def __init__(self, handle, lib):
+        self.h, self.lib = handle, lib
+
+    @classmethod
+    def create(cls, world: int, rank: int, unique_id: Optional[bytes], device: int) -> "Comm":
+        L = load_library()
+        h = C.c_void_p()
+        idbuf = (C.c_uint8 * RT_COMM_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        _check(L.rt_comm_create(world, rank, idbuf, device, C.byref(h)), "rt_comm_create")
+        return cls(h, L)
+
+    @classmethod
+    def create_local(cls, devices) -> list:
+        """One process, len(devices) GPUs: [Comm of rank 0, ...] (rt_comm_create_local)."""
+        L = load_library()
+        n = len(devices)
+        dev = (C.c_int * n)(*devices)
+        hs = (C.c_void_p * n)()
+        _check(L.rt_comm_create_local(n, dev, hs), "rt_comm_create_local")
+        return [cls(C.c_void_p(hs[i]), L) for i in range(n)]
+
+    @property
+    def rank(self) -> int:
+        return int(self.lib.rt_comm_rank(self.h))
+
+    @property
+    def size(self) -> int:
+        return int(self.lib.rt_comm_size(self.h))
+
+    def frame_ptr(self) -> int:
+        return int(self.lib.rt_comm_frame(self.h) or 0)
+
+    def stats(self) -> dict:
+        o = np.zeros(4, np.float64)
+        _check(self.lib.rt_comm_get_stats(self.h, _p(o)), "rt_comm_get_stats")
+        return dict(combine_ms=float(o[0]), deliver_ms=float(o[1]), reduce_bytes=float(o[2]), peer_memory=bool(o[3]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rt_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def render_combined(scene: Scene, comm: Comm, cam, params, width: int, height: int, partition: str = "tiles", tile: int = 32,
+                    flags: int = 0, root: int = 0, want_frame: bool = False, want_rgba8: bool = False, out=None):
+    """rt_render_combined: this rank's share of Render() + the NCCL combine. Returns (frame or None, rgba8 or None, scene_luma or
+    None, counters); the outputs are filled on `root` only."""
+    cam = np.asarray(cam, CAMERA).reshape(1); params = np.asarray(params, PARAMS).reshape(1)
+    is_root = comm.rank == root
+    if not (want_frame and is_root):
+        out = None
+    elif out is None:
+        out = np.empty((height, width, 4), np.float32)
+    out8 = np.empty((height, width, 4), np.uint8) if (want_rgba8 and is_root) else None
+    luma = C.c_float(0)
+    cnt = np.zeros(1, COUNTERS)
+    _check(scene.lib.rt_render_combined(scene.h, comm.h, _p(cam), _p(params), C.c_uint32(width), C.c_uint32(height),
+                                        C.c_int(PARTITIONS[partition]), C.c_uint32(tile), C.c_uint32(flags), C.c_int(root), _p(out), _p(out8),
+                                        C.byref(luma) if out8 is not None else None, _p(cnt)), "rt_render_combined")
+    return out, out8, (float(luma.value) if out8 is not None else None), cnt[0]
+
+
+def render_multi(scenes, comms, cam, params, width: int, height: int, partition: str = "tiles", tile: int = 32, flags: int = 0,
+                 want_rgba8: bool = False):
+    """rt_render_multi: Render() on len(scenes) GPUs of this process. Returns (frame (H, W, 4), rgba8 or None, scene_luma or None, counters)."""
+    cam = np.asarray(cam, CAMERA).reshape(1); params = np.asarray(params, PARAMS).reshape(1)
+    n = len(scenes)
+    sh = (C.c_void_p * n)(*[s.h for s in scenes]); ch = (C.c_void_p * n)(*[c.h for c in comms])
+    out = np.empty((height, width, 4), np.float32)
+    out8 = np.empty((height, width, 4), np.uint8) if want_rgba8 else None
+    luma = C.c_float(0)
+    cnt = np.zeros(1, COUNTERS)
+    _check(scenes[0].lib.rt_render_multi(sh, ch, C.c_int(n), _p(cam), _p(params), C.c_uint32(width), C.c_uint32(height),
+                                         C.c_int(PARTITIONS[partition]), C.c_uint32(tile), C.c_uint32(flags), _p(out), _p(out8),
+                                         C.byref(luma) if want_rgba8 else None, _p(cnt)), "rt_render_multi")
+    return out, out8, (float(luma.value) if want_rgba8 else None), cnt[0]

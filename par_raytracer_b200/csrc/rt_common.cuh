@@ -42,6 +42,12 @@ RT_DEVICE float clampf(float n, float a, float b) {                             
     return m < b ? m : b;
 }
 
+RT_DEVICE f3 ld3(const float *p, uint32_t i) { return mk3(p[3 * (size_t)i], p[3 * (size_t)i + 1], p[3 * (size_t)i + 2]); }
+RT_DEVICE uint32_t find_group(const uint32_t *group_first, uint32_t n_groups, uint32_t index) {
+    uint32_t lo = 0, hi = n_groups;     // last g with group_first[g] <= index
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (group_first[mid] <= index) lo = mid; else hi = mid; }
+    return lo;
+}
 RT_DEVICE float4 mk4(f3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 RT_DEVICE float4 mk4u(f3 v, uint32_t w) { return make_float4(v.x, v.y, v.z, __uint_as_float(w)); }
 
@@ -148,5 +154,10 @@ struct DevParams {
     uint32_t pad;
     uint64_t base_seed;
 };
+
+#define RT_BOUNDS_SPHERE 0        // child bound of the traversal (rt_trace.cuh): sphere + slab, float boxes, boxes on the 15-bit scene grid
+#define RT_BOUNDS_BOX 1
+#define RT_BOUNDS_QBOX 2
+#define RT_STACK_MAX 64           // traversal stack entries per ray; the build guarantees depth + 2 <= RT_STACK_MAX
 
 #define RT_SEED_MULT 0x9E3779B97F4A7C15ULL

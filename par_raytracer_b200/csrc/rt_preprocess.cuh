@@ -6,7 +6,7 @@
 //     rounded to float (glibc's float powf is correctly rounded in all but rare cases), then truncated like (u8)(x * 255).
 #pragma once
 #include "rt_common.cuh"
-#include "rt_build.cuh"      // ld3, bitonic sort kernels
+#include "rt_sort.cuh"       // bitonic sort kernels
 
 struct TangentInput {
     const float *positions, *texcoords;

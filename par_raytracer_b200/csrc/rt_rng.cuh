@@ -38,7 +38,7 @@ RT_DEVICE uint64_t rng_step(uint64_t s0, uint64_t s1) { // random.h:35-39 (note 
     return s0 ^ s1;
 }
 
-__device__ __noinline__ uint64_t rng_replay(uint64_t seed, uint32_t n) {   // value of draw index n (0-based)
+static __device__ __noinline__ uint64_t rng_replay(uint64_t seed, uint32_t n) {   // value of draw index n (0-based)
     uint64_t st[16];
     uint64_t x = seed;
     for (int i = 0; i < 16; ++i) { x = rng_xs(x); st[i] = x * 2685821657736338717ULL; }

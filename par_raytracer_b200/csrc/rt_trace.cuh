@@ -17,22 +17,10 @@
 #pragma once
 #include "rt_common.cuh"
 #include "rt_raygen.cuh"
+#include "rt_types.cuh"
 
-#define RT_STACK_MAX 64
 #define RT_CULL_SLACK 4e-6f
 
-struct RayQueue {              // SoA ray stream: 32 B per ray
-    float4 *o;                 // origin.xyz (unbiased, as handed to TraceRay), w: kernel specific
-    float4 *d;                 // direction.xyz, w: slot / flags bits
-};
-
-struct HitRec {                // 16 B per ray
-    float t;
-    float v, w;                // bw.y, bw.z numerators already divided (raytracer.cpp:118-119)
-    int32_t tri;               // cluster-order triangle index, -1 = miss
-};
-
-struct TraceCounters { unsigned long long sphere_checks, cluster_checks; };
 
 RT_DEVICE float approx_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RT_DEVICE float approx_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // culling only: 1 MUFU
@@ -128,9 +116,6 @@ RT_DEVICE bool box_child(float lx, float ly, float lz, float hx, float hy, float
 // axis word, so the ray's direction signs choose near and far planes up front and the per-axis min / max disappears: a node
 // visit costs about what the float-box visit costs, with half the bytes and half the load instructions. The per-ray slack
 // moves the near plane towards the origin side and the far plane away from it (cn / cf), as in box_ray_setup.
-#define RT_BOUNDS_SPHERE 0
-#define RT_BOUNDS_BOX 1
-#define RT_BOUNDS_QBOX 2
 struct QRay { float ax, ay, az, cnx, cny, cnz, cfx, cfy, cfz; uint32_t snx, sny, snz; };   // s?: near selector; far = near ^ 0x0220
 
 RT_DEVICE void qbox_ray_setup(QRay &Q, const DevScene &S, f3 o, f3 d, float slack) {
@@ -190,24 +175,6 @@ RT_DEVICE bool qbox_child(uint32_t wx, uint32_t wy, uint32_t wz, const QRay &Q, 
 #endif
 #define RT_DONE ((int)0x80000000)      // never a leaf ref: |leaf ref| <= 1 + 8 * 2e8 + 7 < 2^31
 
-struct WaveQueues {
-    RayQueue closest;              // d.w = path slot
-    const uint32_t *n_closest;     // device-side count (NULL: closest_max rays)
-    uint32_t closest_max;
-    HitRec *hits;
-    const float4 *shadow_o;        // light l owns [l * shadow_stride, ...): origin.xyz, w = path slot
-    const float4 *shadow_dir;      // NULL: direction = f(light, origin) as GetShadowRayForLight (raytracer.cpp:234-250); else explicit
-    const float4 *rad;             // radiance to add when the light is visible; w = light_dist_sq (point light) or < 0
-    const uint32_t *n_shadow;      // [n_lights] device-side counts
-    uint32_t shadow_stride, n_lights;
-    float4 *acc;                   // light 0 adds into the path accumulator ...
-    float4 *acc_extra;             // ... light l >= 1 into acc_extra[(l - 1) * shadow_stride + slot] (single writer each: no atomics)
-    uint32_t *next;                // work counter, zero before launch
-    uint32_t fetch_min;            // refill the warp once this many lanes are idle (32 = only when all are): bounce rays
-    uint32_t fetch_min_primary;    // same while the work counter is still inside the primary rays of wave 0
-    uint32_t fetch_min_shadow;     // same inside the shadow-ray region
-    uint32_t leaf_wait;            // leave the node loop once this many live lanes wait at a cluster / have finished (32: only when all do)
-};
 
 template <bool COUNT, int BOUNDS>
 __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_wave(DevScene S, float bias, WaveQueues W, PrimaryGen G, TraceCounters *counters) {

@@ -1,4 +1,6 @@
-"""Multi-GPU partition + combine for the render path (one process per GPU, torch.distributed/NCCL).
+"""Multi-GPU partition + combine for the render path, one process per GPU. The product path is the C ABI
+(rt_comm_* / rt_render_combined: NCCL C API on the render stream + resolve kernel); torch.distributed only carries the
+128-byte NCCL unique id between the processes. `combine_frame` is the host-side model used by the gloo CPU tests.
 
 The reference shards contiguous pixel-index ranges over MPI ranks with the scene replicated and gathers
 the ranges on rank 0 (main.cpp:311-319, 345-347). Here:
@@ -31,17 +33,10 @@ def range_partition(width: int, height: int, rank: int, world: int) -> Tuple[int
 
 def tile_partition(width: int, height: int, rank: int, world: int, tile: int = 32) -> np.ndarray:
     """Linear pixel ids (row-major, uint32) of the tiles owned by `rank`: tile t = ty * tiles_x + tx goes to
-    rank t % world. Inside a tile pixels are listed row by row, so a warp's rays stay coherent."""
-    tiles_x = (width + tile - 1) // tile
-    tiles_y = (height + tile - 1) // tile
-    ids = []
-    for t in range(rank, tiles_x * tiles_y, world):
-        ty, tx = divmod(t, tiles_x)
-        x0, y0 = tx * tile, ty * tile
-        xs = np.arange(x0, min(x0 + tile, width), dtype=np.uint32)
-        ys = np.arange(y0, min(y0 + tile, height), dtype=np.uint32)
-        ids.append((ys[:, None] * np.uint32(width) + xs[None, :]).reshape(-1))
-    return np.concatenate(ids).astype(np.uint32) if ids else np.zeros(0, np.uint32)
+    rank t % world; inside a tile pixels are listed row by row, so a warp's rays stay coherent. Computed by the
+    library's own host function (rt_partition_tiles), the one rt_render_combined uses."""
+    from . import api
+    return api.partition_tiles(width, height, rank, world, tile)
 
 
 def sample_partition(total_samples: int, rank: int, world: int) -> Tuple[int, int]:
@@ -52,9 +47,8 @@ def sample_partition(total_samples: int, rank: int, world: int) -> Tuple[int, in
 
 
 def combine_frame(local_frame, mode: str, total_samples: int, dst: int = 0, group=None):
-    """The collective that replaces MPI_Gather. `local_frame` is a (H*W, 4) float32 torch tensor (cuda+nccl
-    or cpu+gloo) holding this rank's pixels (tiles/ranges: resolved colours, zeros elsewhere; samples: raw
-    sums, w = samples rendered). After the call rank `dst` holds the finished frame in `local_frame`."""
+    """Host-side MODEL of the combine for CPU (gloo) runs of the partition logic: reduce(SUM) to `dst`, then the resolve the
+    partition implies. On GPUs the product path is rt_render_combined (NCCL C API + resolve kernel inside the library)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(local_frame, dst=dst, op=dist.ReduceOp.SUM, group=group)
@@ -67,10 +61,9 @@ def combine_frame(local_frame, mode: str, total_samples: int, dst: int = 0, grou
     return local_frame
 
 
-def render_distributed(scene, cam, params, width: int, height: int, mode: str = "tiles", tile: int = 32,
-                       rank: Optional[int] = None, world: Optional[int] = None, device=None, frame=None, group=None):
-    """Render(cam, scene, w, h) over all ranks of the process group. Returns (frame tensor, counters, gpu_ms).
-    The frame is complete on rank 0 only (like Framebuffer.pixels, main.cpp:338-340)."""
+def make_comm(device: int, rank: Optional[int] = None, world: Optional[int] = None, group=None):
+    """rt_comm for this rank of the torch.distributed job: rank 0 draws the NCCL unique id (rt_comm_unique_id), the process
+    group's own broadcast hands it out (an MPI host would use one MPI_Bcast), every rank calls rt_comm_create."""
     import torch
     import torch.distributed as dist
     from . import api
@@ -78,27 +71,20 @@ def render_distributed(scene, cam, params, width: int, height: int, mode: str = 
         rank = dist.get_rank(group) if dist.is_initialized() else 0
     if world is None:
         world = dist.get_world_size(group) if dist.is_initialized() else 1
-    device = device if device is not None else torch.device("cuda", scene.device)
-    if frame is None:
-        frame = torch.zeros((width * height, 4), dtype=torch.float32, device=device)
-    else:
-        frame.zero_()
-    spp = int(np.asarray(params)["min_samples"])
-    stream = torch.cuda.current_stream(device).cuda_stream
-    if mode == "tiles":
-        ids = tile_partition(width, height, rank, world, tile)
-        cnt = scene.render_device(cam, params, width, height, frame.data_ptr(), pixel_ids=ids, sample_count=spp,
-                                  flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME, stream=stream)
-    elif mode == "ranges":
-        start, count = range_partition(width, height, rank, world)
-        cnt = scene.render_device(cam, params, width, height, frame.data_ptr(), pixel_begin=start, pixel_count=count,
-                                  sample_count=spp, flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME, stream=stream)
-    elif mode == "samples":
-        s0, ns = sample_partition(spp, rank, world)
-        cnt = scene.render_device(cam, params, width, height, frame.data_ptr(), pixel_begin=0, pixel_count=width * height,
-                                  sample_begin=s0, sample_count=ns, flags=api.RT_OUT_SUM | api.RT_OUT_FULLFRAME, stream=stream)
-    else:
-        raise ValueError(f"unknown mode {mode!r}")
-    gpu_ms = float(scene.stats()["gpu_ms"])
-    combine_frame(frame, mode, spp, dst=0, group=group)
-    return frame, cnt, gpu_ms
+    uid = None
+    if world > 1:
+        box = [api.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = box[0]
+    return api.Comm.create(world, rank, uid, device)
+
+
+def render_distributed(scene, comm, cam, params, width: int, height: int, mode: str = "tiles", tile: int = 32, flags: int = 0,
+                       want_frame: bool = True):
+    """Render(cam, scene, w, h) over all ranks of `comm`: one rt_render_combined call per rank. Returns (frame (H, W, 4) float32
+    on rank 0 / None elsewhere, counters, gpu_ms of this rank's render). Like Framebuffer.pixels the frame exists on rank 0 only
+    (main.cpp:338-340)."""
+    from . import api
+    frame, _, _, cnt = api.render_combined(scene, comm, cam, params, width, height, partition=mode, tile=tile, flags=flags, root=0,
+                                           want_frame=want_frame)
+    return frame, cnt, float(scene.stats()["gpu_ms"])

@@ -117,24 +117,100 @@ inline void Flatten(Scene * scene, FlatScene * f) {
     d.n_lights = scene->light_count;          d.lights = (const rt_light *)scene->lights;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-resident scenes are kept between RenderB200 calls (creating one uploads the mesh and builds the GPU hierarchy: up to
+// 0.24 s at 10 M triangles, and each owns a multi-GB path pool), keyed by the reference's Scene pointer. RenderB200Shutdown()
+// frees them; the reference itself never frees anything (ownership).
+// ---------------------------------------------------------------------------------------------------------------------
+struct DeviceSet {
+    Scene * key;
+    std::vector<rt_scene *> scenes;      // one per GPU this rank drives
+    std::vector<rt_comm *> comms;        // local group (CommSize == 1) or one NCCL rank (CommSize > 1)
+    bool nccl_ranks;                     // comms[0] spans the MPI ranks
+};
+inline std::vector<DeviceSet> & DeviceSets() { static std::vector<DeviceSet> v; return v; }
+
+inline void RenderB200Shutdown() {
+    std::vector<DeviceSet> & v = DeviceSets();
+    for (size_t i = 0; i < v.size(); ++i) {
+        for (size_t k = 0; k < v[i].comms.size(); ++k) rt_comm_destroy(v[i].comms[k]);
+        for (size_t k = 0; k < v[i].scenes.size(); ++k) rt_scene_destroy(v[i].scenes[k]);
+    }
+    v.clear();
+}
+
+// every rank agrees on failure BEFORE entering a collective (a rank that returned early would hang the others' MPI_Gather /
+// ncclReduce): min over ranks of the status codes
+inline int AgreeStatus(int rc) {
+    int all = rc;
+    if (gMPI_CommSize > 1) MPI_Allreduce(&rc, &all, 1, MPI_INT, MPI_MIN, MPI_COMM_WORLD);
+    return all;
+}
+
+inline DeviceSet * GetDeviceSet(Scene * scene, int device_override) {
+    std::vector<DeviceSet> & v = DeviceSets();
+    for (size_t i = 0; i < v.size(); ++i) if (v[i].key == scene) return &v[i];
+    DeviceSet ds;
+    ds.key = scene; ds.nccl_ranks = false;
+    int ndev = rt_device_count();
+    int rc = ndev > 0 ? RT_OK : RT_ERR_CUDA;
+    if (rc != RT_OK) fprintf(stderr, "RenderB200: no CUDA device (there is no CPU fallback)\n");
+    FlatScene flat;
+    if (rc == RT_OK) Flatten(scene, &flat);
+    std::vector<int> devices;
+    if (rc == RT_OK) {
+        if (gMPI_CommSize > 1 || device_override >= 0) devices.push_back(device_override >= 0 ? device_override : gMPI_CommRank % ndev);   // one GPU per rank, wrapping
+        else for (int d = 0; d < ndev; ++d) devices.push_back(d);                // a single rank drives every GPU of the node
+        for (size_t k = 0; k < devices.size() && rc == RT_OK; ++k) {
+            rt_scene * h = NULL;
+            rc = rt_scene_create(&flat.desc, devices[k], &h);
+            if (rc != RT_OK) fprintf(stderr, "rt_scene_create (GPU %d) failed: %s\n", devices[k], rt_last_error());
+            else ds.scenes.push_back(h);
+        }
+    }
+    if (rc == RT_OK && gMPI_CommSize == 1) {
+        ds.comms.resize(devices.size(), NULL);
+        rc = rt_comm_create_local((int)devices.size(), devices.data(), ds.comms.data());
+        if (rc != RT_OK) { fprintf(stderr, "rt_comm_create_local failed: %s\n", rt_last_error()); ds.comms.clear(); }
+    }
+    rc = AgreeStatus(rc);
+    if (rc == RT_OK && gMPI_CommSize > 1) {
+        // NCCL across the MPI ranks: rank 0 draws the id, one MPI_Bcast hands it out. If NCCL is not available the ranks agree to keep
+        // the reference's host-side MPI_Gather (a transport choice; the rendering is on the GPU either way).
+        uint8_t id[RT_COMM_ID_BYTES];
+        memset(id, 0, sizeof(id));
+        int have = gMPI_CommRank == 0 ? (rt_comm_unique_id(id) == RT_OK ? 1 : 0) : 1;
+        MPI_Bcast(&have, 1, MPI_INT, 0, MPI_COMM_WORLD);
+        if (have) {
+            MPI_Bcast(id, RT_COMM_ID_BYTES, MPI_BYTE, 0, MPI_COMM_WORLD);
+            rt_comm * c = NULL;
+            int rcc = rt_comm_create(gMPI_CommSize, gMPI_CommRank, id, devices[0], &c);
+            if (rcc != RT_OK) fprintf(stderr, "rt_comm_create failed: %s\n", rt_last_error());
+            rc = AgreeStatus(rcc);
+            if (c) ds.comms.push_back(c);
+            ds.nccl_ranks = rc == RT_OK;
+        }
+    }
+    if (rc != RT_OK) {
+        for (size_t k = 0; k < ds.comms.size(); ++k) if (ds.comms[k]) rt_comm_destroy(ds.comms[k]);
+        for (size_t k = 0; k < ds.scenes.size(); ++k) rt_scene_destroy(ds.scenes[k]);
+        return NULL;
+    }
+    v.push_back(ds);
+    return &v.back();
+}
+
 // Defaults = Render's hard-coded adaptive 10..50 samples (main.cpp:308-309); min_samples == max_samples gives the fixed-spp
-// mean; base_seed: see rt_params in rt_b200.h.
+// mean; base_seed: see rt_params in rt_b200.h. device < 0: GPU = rank % GPUs of the node when there are several MPI ranks, ALL GPUs
+// of the node (rt_render_multi) when there is one.
 inline Framebuffer RenderB200(Camera * cam, Scene * scene, u32 width, u32 height, u32 min_samples = 10, u32 max_samples = 50,
                               u64 base_seed = 0x835fdd9143716fe3ULL, int device = -1, rt_counters * out_counters = NULL) {
     Framebuffer result;
     result.width = width; result.height = height; result.pixels = NULL;
     static_assert(sizeof(Camera) == sizeof(rt_camera), "Camera layout");
 
-    FlatScene flat;
-    Flatten(scene, &flat);
-    rt_scene * handle = NULL;
-    if (device < 0) device = gMPI_CommRank;             // one GPU per rank; wraps below if the node has fewer
-    int rc = rt_scene_create(&flat.desc, device, &handle);
-    if (rc == RT_ERR_ARG && device > 0) rc = rt_scene_create(&flat.desc, 0, &handle);
-    if (rc != RT_OK) {
-        fprintf(stderr, "rt_scene_create failed: %s\n", rt_last_error());     // no CPU fallback: report and return an empty frame
-        return result;
-    }
+    DeviceSet * ds = GetDeviceSet(scene, device);          // collective; NULL on every rank if any rank failed
+    if (!ds) return result;                                // no CPU fallback: an empty frame, reported above
     rt_params params;
     params.ray_bias = gParams.ray_bias;
     params.reflection_samples = gParams.reflection_samples;
@@ -143,33 +219,58 @@ inline Framebuffer RenderB200(Camera * cam, Scene * scene, u32 width, u32 height
     memcpy(params.background_color, &gParams.background_color, 16);
     params.min_samples = min_samples; params.max_samples = max_samples;
     params.base_seed = base_seed;
+    const u32 flags = min_samples < max_samples ? RT_FLAG_ADAPTIVE : 0u;
+    const u32 tile = 32;
 
     u32 total_pixel_count = width * height;                                      // main.cpp:311-317
     u32 count_per_proc = (total_pixel_count + gMPI_CommSize - 1) / gMPI_CommSize;
-    u32 start_idx = count_per_proc * gMPI_CommRank;
-    u32 count = start_idx < total_pixel_count ? (start_idx + count_per_proc <= total_pixel_count ? count_per_proc : total_pixel_count - start_idx) : 0;
-    Vector4 * buffer = (Vector4 *)calloc(sizeof(Vector4), count_per_proc);       // main.cpp:318
     rt_counters counters;
     memset(&counters, 0, sizeof(counters));
-    {
+    int rc = RT_OK;
+    if (gMPI_CommRank == 0) result.pixels = (Vector4 *)calloc(sizeof(Vector4), (size_t)count_per_proc * gMPI_CommSize);   // main.cpp:338-340
+
+    if (gMPI_CommSize == 1) {
+        // one rank: every GPU of the node renders interleaved tiles, gathered through peer memory (or NCCL) inside the library
         MPI_Barrier(MPI_COMM_WORLD);                                             // main.cpp:326-333
         TIME_BLOCK("Render, sync");
-        rc = rt_render(handle, (const rt_camera *)cam, &params, width, height, NULL, start_idx, count, 0, min_samples,
-                       RT_OUT_MEAN | (min_samples < max_samples ? RT_FLAG_ADAPTIVE : 0u), (float *)buffer, &counters);
-        if (rc != RT_OK) fprintf(stderr, "rt_render failed: %s\n", rt_last_error());
+        rc = rt_render_multi(ds->scenes.data(), ds->comms.data(), (int)ds->scenes.size(), (const rt_camera *)cam, &params, width, height,
+                             RT_PART_TILES, tile, flags, (float *)result.pixels, NULL, NULL, &counters);
+        if (rc != RT_OK) fprintf(stderr, "rt_render_multi failed: %s\n", rt_last_error());
         MPI_Barrier(MPI_COMM_WORLD);
-    }
-    if (gMPI_CommRank == 0) result.pixels = (Vector4 *)calloc(sizeof(Vector4), (size_t)count_per_proc * gMPI_CommSize);   // main.cpp:338-340
-    {
-        TIME_BLOCK("Reduce");
-        MPI_Gather(buffer, count_per_proc * 4, MPI_FLOAT, result.pixels, count_per_proc * 4, MPI_FLOAT, 0, MPI_COMM_WORLD);   // main.cpp:345-347
+    } else if (ds->nccl_ranks) {
+        // several ranks, NCCL: interleaved tiles (contiguous ranges load-balance badly, NOTES.txt:25), ncclReduce to rank 0 on the render
+        // stream instead of staging every rank's pixels through host memory for MPI_Gather (main.cpp:345-347)
         MPI_Barrier(MPI_COMM_WORLD);
+        TIME_BLOCK("Render + reduce, sync");
+        rc = rt_render_combined(ds->scenes[0], ds->comms[0], (const rt_camera *)cam, &params, width, height, RT_PART_TILES, tile, flags, 0,
+                                (float *)result.pixels, NULL, NULL, &counters);
+        if (rc != RT_OK) fprintf(stderr, "rt_render_combined failed: %s\n", rt_last_error());
+        MPI_Barrier(MPI_COMM_WORLD);
+    } else {
+        // several ranks without NCCL: the reference's own contiguous ranges and its MPI_Gather
+        u32 start_idx = count_per_proc * gMPI_CommRank;
+        u32 count = start_idx < total_pixel_count ? (start_idx + count_per_proc <= total_pixel_count ? count_per_proc : total_pixel_count - start_idx) : 0;
+        Vector4 * buffer = (Vector4 *)calloc(sizeof(Vector4), count_per_proc);   // main.cpp:318
+        {
+            MPI_Barrier(MPI_COMM_WORLD);
+            TIME_BLOCK("Render, sync");
+            rc = rt_render(ds->scenes[0], (const rt_camera *)cam, &params, width, height, NULL, start_idx, count, 0, min_samples,
+                           RT_OUT_MEAN | flags, (float *)buffer, &counters);
+            if (rc != RT_OK) fprintf(stderr, "rt_render failed: %s\n", rt_last_error());
+            MPI_Barrier(MPI_COMM_WORLD);
+        }
+        {
+            TIME_BLOCK("Reduce");
+            MPI_Gather(buffer, count_per_proc * 4, MPI_FLOAT, result.pixels, count_per_proc * 4, MPI_FLOAT, 0, MPI_COMM_WORLD);   // main.cpp:345-347
+            MPI_Barrier(MPI_COMM_WORLD);
+        }
+        free(buffer);
     }
+    rc = AgreeStatus(rc);                                                        // a failed rank's zeros are not a frame
+    if (rc != RT_OK) { free(result.pixels); result.pixels = NULL; return result; }
     printf("Process %d\n", gMPI_CommRank);                                       // main.cpp:351-356
     printf("Rays cast:          %llu\n", (unsigned long long)counters.ray_count);
     if (out_counters) *out_counters = counters;
-    free(buffer);
-    rt_scene_destroy(handle);
     return result;
 }
 

@@ -210,7 +210,10 @@ class MeshBuilder:
         gm = np.array([g[1] for g in self.groups], dtype=np.int32)
         has_bump = [m >= 0 and materials[m]["bump_texture"] >= 0 for m in gm]
         tangents = calculate_tangents(positions, texcoords, normals, gf, ip, it, inn, has_bump) if any(has_bump) else None
-        spheres, sg = hierarchy if hierarchy is not None else build_group_hierarchy(positions, gf, ip)
+        if isinstance(hierarchy, str) and hierarchy == "defer":     # filled in later by use_reference_hierarchy() (BuildHierarchy on the GPU)
+            spheres, sg = np.zeros(0, BSPHERE), np.zeros(0, np.int32)
+        else:
+            spheres, sg = hierarchy if hierarchy is not None else build_group_hierarchy(positions, gf, ip)
         sd = SceneData(positions=positions, texcoords=texcoords, normals=normals, tangents=tangents, group_first=gf,
                        idx_positions=ip, idx_texcoords=it, idx_normals=inn, group_material=gm, spheres=spheres,
                        sphere_group=sg, materials=materials, default_material=default_material(), textures=textures,
@@ -361,8 +364,8 @@ def spheres_plane_scene(grid: int = 4, nu: int = 64, nv: int = 32, spacing: floa
 
 
 def heightfield_scene(cells_x: int = 64, cells_z: int = 64, block: int = 16, size: float = 100.0, amp: float = 6.0,
-                      textured: bool = True, tex_size: int = 128, name: str = "heightfield", seed: int = 20170218
-                      ) -> SceneData:
+                      textured: bool = True, tex_size: int = 128, name: str = "heightfield", seed: int = 20170218,
+                      hierarchy=None) -> SceneData:
     """BASELINE configs 3/4/5 style: a height-field terrain of 2*cells_x*cells_z triangles, grouped in
     block x block cell tiles (2*block^2 triangles per group), ~8 cycling materials (diffuse/ambient maps,
     bump map, one alpha mask). Vertex streams are shared between groups like a real OBJ."""
@@ -427,9 +430,19 @@ def heightfield_scene(cells_x: int = 64, cells_z: int = 64, block: int = 16, siz
             tris[1::2] = t1
             mb.add_group_shared(f"tile{gi}", gi % len(mats), tris, tris, tris)
             gi += 1
-    sd = mb.finish(np.array(mats, dtype=MATERIAL), textures, name=name)
+    sd = mb.finish(np.array(mats, dtype=MATERIAL), textures, name=name, hierarchy=hierarchy)
     zext = size * (cells_z / cells_x)
     sd.camera_hint = dict(position=(0.0, amp * 3.0 + 0.12 * size, 0.55 * zext), facing=(0.0, -0.45, -1.0), fov=60.0)  # type: ignore[attr-defined]
+    return sd
+
+
+def use_reference_hierarchy(sd: SceneData, device: int = 0) -> SceneData:
+    """Replaces sd.spheres / sd.sphere_group by the reference's OWN hierarchy over the mesh groups -- BuildHierarchy
+    (bsphere.cpp:379-444) run on the GPU by rt_build_group_hierarchy, bit-identical to the host build (tests/test_gpu_parity.py) --
+    so that the equal-t tie-break order is exactly what the unmodified reference derives from the same OBJ."""
+    from . import api
+    sd.spheres, sd.sphere_group = api.build_group_hierarchy(sd, device)
+    sd.validate()
     return sd
 
 

@@ -192,8 +192,9 @@ class SceneData:
             assert self.idx_texcoords.max() < len(self.texcoords)
             assert self.idx_normals.max() < len(self.normals)
         assert self.spheres.size == self.sphere_group.size
-        leaves = self.sphere_group[self.sphere_group >= 0]
-        assert sorted(leaves.tolist()) == list(range(self.n_groups)), "every group must be exactly one leaf"
+        if self.spheres.size:                        # empty: no reference hierarchy (tie-break rank = group order)
+            leaves = self.sphere_group[self.sphere_group >= 0]
+            assert sorted(leaves.tolist()) == list(range(self.n_groups)), "every group must be exactly one leaf"
         assert np.all(self.group_material < len(self.materials))
 
     # ---- (de)serialisation for tests/golden fixtures -------------------------------------------

@@ -1,0 +1,52 @@
+"""rt_render_combined / rt_render_multi on ONE GPU (a 1-rank group): partition + render + resolve + tone map + download inside the
+library must reproduce the plain rt_render frame -- the single-rank case of Render()'s partition and MPI_Gather (main.cpp:311-319,
+345-347; with CommSize == 1 the gather is a copy). The N-rank cases are tests/test_gpu_multi.py (>= 2 GPUs) and bench.py's
+`combine_parity` self-check."""
+import numpy as np
+import pytest
+
+from par_raytracer_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["tiles", "ranges", "samples"])
+def test_one_rank_combined_equals_render(golden_scene, mode):
+    gs = golden_scene
+    S = api.Scene(gs.scene)
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
+    want, cnt_w = S.render(gs.cam, p, gs.W, gs.H)
+    comm = api.Comm.create(1, 0, None, 0)
+    frame, rgba8, luma, cnt = api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, partition=mode, tile=8, want_frame=True, want_rgba8=True)
+    assert int(cnt["ray_count"]) == int(cnt_w["ray_count"]) == int(gs.render_counters["ray_count"])
+    if mode == "samples":       # sum / n in the resolve kernel == k_finalize's sum / n
+        assert np.array_equal(frame.view(np.uint32), want.view(np.uint32))
+    else:
+        assert np.array_equal(frame.view(np.uint32), want.view(np.uint32))
+    assert np.allclose(frame.reshape(-1, 4), gs.render_rgba, rtol=1e-5, atol=1e-6)
+    want8, want_luma = api.tonemap(want)
+    assert np.array_equal(rgba8, want8) and luma == want_luma
+    st = comm.stats()
+    assert st["reduce_bytes"] == 0 and not st["peer_memory"]
+    # the local (one process) group of one GPU goes through rt_render_multi
+    comms = api.Comm.create_local([0])
+    frame2, _, _, cnt2 = api.render_multi([S], comms, gs.cam, p, gs.W, gs.H, partition=mode, tile=8)
+    assert np.array_equal(frame2.view(np.uint32), want.view(np.uint32)) and int(cnt2["ray_count"]) == int(cnt_w["ray_count"])
+    comms[0].close(); comm.close(); S.close()
+
+
+def test_combined_adaptive_and_argument_errors(golden_scene):
+    gs = golden_scene
+    S = api.Scene(gs.scene)
+    comm = api.Comm.create(1, 0, None, 0)
+    p = gs.params.copy(); p["min_samples"], p["max_samples"] = gs.adaptive_minmax
+    frame, _, _, cnt = api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, partition="tiles", tile=16, flags=api.RT_FLAG_ADAPTIVE, want_frame=True)
+    want, cnt_w = S.render(gs.cam, p, gs.W, gs.H, flags=api.RT_FLAG_ADAPTIVE)
+    assert np.array_equal(frame.view(np.uint32), want.view(np.uint32)) and int(cnt["ray_count"]) == int(cnt_w["ray_count"])
+    with pytest.raises(api.RtError, match="adaptive"):
+        api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, partition="samples", flags=api.RT_FLAG_ADAPTIVE)
+    with pytest.raises(api.RtError):
+        api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, partition="tiles", tile=0)
+    with pytest.raises(api.RtError):
+        api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, root=3)
+    comm.close(); S.close()

@@ -24,12 +24,11 @@ def _worker(rank, world, port, mode, out_path):
     gs = GoldenScene("spheres")
     S = api.Scene(gs.scene, device=rank)
     p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
-    frame, cnt, _ = dist.render_distributed(S, gs.cam, p, gs.W, gs.H, mode=mode, tile=8, rank=rank, world=world)
-    rays = torch.tensor([int(cnt["ray_count"])], dtype=torch.int64, device=f"cuda:{rank}")
-    dist_t.all_reduce(rays)
+    comm = dist.make_comm(rank, rank, world)
+    frame, cnt, _ = dist.render_distributed(S, comm, gs.cam, p, gs.W, gs.H, mode=mode, tile=8)
     if rank == 0:
-        np.save(out_path, frame.cpu().numpy())
-        np.save(out_path + ".rays.npy", rays.cpu().numpy())
+        np.save(out_path, frame.reshape(-1, 4))
+        np.save(out_path + ".rays.npy", np.array([int(cnt["ray_count"])]))      # rt_render_combined sums the counters on the root
     dist_t.barrier()
     dist_t.destroy_process_group()
 
@@ -50,3 +49,34 @@ def test_nccl_combine_equals_single_gpu(tmp_path, mode):
     assert rays == int(gs.render_counters["ray_count"])
     assert np.allclose(frame, want, rtol=1e-5, atol=1e-6)
     assert np.all(frame[:, 3] == 1.0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("mode", ["tiles", "ranges", "samples"])
+@pytest.mark.parametrize("p2p", [True, False])
+def test_render_multi_single_process(mode, p2p, monkeypatch):
+    """rt_render_multi (one process, 2 GPUs): the peer-memory gather and the NCCL fallback against the single-GPU render of the
+    same frame -- bit-exact for the pixel partitions (the gather moves bits), 2e-6 for the sample split (a different sum tree)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import GoldenScene
+    from par_raytracer_b200 import api
+    gs = GoldenScene("spheres")
+    if not p2p:
+        monkeypatch.setenv("RT_B200_NO_P2P", "1")
+    scenes = [api.Scene(gs.scene, device=d) for d in range(2)]
+    comms = api.Comm.create_local([0, 1])
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
+    single, cnt1 = scenes[0].render(gs.cam, p, gs.W, gs.H)
+    frame, rgba8, luma, cnt = api.render_multi(scenes, comms, gs.cam, p, gs.W, gs.H, partition=mode, tile=8, want_rgba8=True)
+    assert comms[0].stats()["peer_memory"] == p2p
+    assert int(cnt["ray_count"]) == int(cnt1["ray_count"]) == int(gs.render_counters["ray_count"])
+    if mode == "samples":
+        assert np.allclose(frame, single, rtol=2e-6, atol=1e-7) and np.all(frame[..., 3] == 1.0)
+    else:
+        assert np.array_equal(frame.view(np.uint32), single.view(np.uint32))
+    want8, want_luma = api.tonemap(frame)
+    assert np.array_equal(rgba8, want8) and abs(luma - want_luma) <= 1e-6 * abs(want_luma)
+    for c in comms:
+        c.close()
+    for s in scenes:
+        s.close()

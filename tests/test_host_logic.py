@@ -63,6 +63,31 @@ def test_partitions_cover_the_frame_exactly_once():
     assert dist.range_partition(720, 480, 5, 64) == (5 * 5400, 5400)
 
 
+def test_c_tile_partition_matches_numpy_statement():
+    """rt_partition_tiles (host-only C, the partition rt_render_combined uses) against a plain numpy statement of the rule:
+    tile t = ty * tiles_x + tx goes to rank t % world, pixels inside a tile row by row; ragged right / bottom tiles clipped."""
+    from par_raytracer_b200 import api
+
+    def numpy_tiles(width, height, rank, world, tile):
+        tiles_x = (width + tile - 1) // tile
+        tiles_y = (height + tile - 1) // tile
+        ids = []
+        for t in range(rank, tiles_x * tiles_y, world):
+            ty, tx = divmod(t, tiles_x)
+            xs = np.arange(tx * tile, min(tx * tile + tile, width), dtype=np.uint32)
+            ys = np.arange(ty * tile, min(ty * tile + tile, height), dtype=np.uint32)
+            ids.append((ys[:, None] * np.uint32(width) + xs[None, :]).reshape(-1))
+        return np.concatenate(ids).astype(np.uint32) if ids else np.zeros(0, np.uint32)
+
+    for (W, H, tile, world) in [(100, 37, 16, 3), (1920, 1080, 32, 8), (7, 5, 32, 2), (64, 64, 8, 1), (33, 1, 4, 5)]:
+        for r in range(world):
+            assert np.array_equal(api.partition_tiles(W, H, r, world, tile), numpy_tiles(W, H, r, world, tile)), (W, H, tile, world, r)
+    with pytest.raises(api.RtError):
+        api.partition_tiles(10, 10, 2, 2, 4)            # rank out of range
+    with pytest.raises(api.RtError):
+        api.partition_tiles(10, 10, 0, 1, 0)            # tile 0
+
+
 def test_png_writer_roundtrip():
     PIL = pytest.importorskip("PIL.Image")
     rng = np.random.default_rng(0)
