@@ -419,6 +419,75 @@ __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, con
     nodes[kept_index[v]] = o;
 }
 
+// ---- 4b. collapse to the 4-wide form -------------------------------------------------------------------------
+// Level-synchronous, top-down: the frontier holds the binary nodes that become wide nodes of this level. k_wide_expand fills a wide
+// node's four slots -- start from the two binary children, replace the internal child with the largest box by ITS two children until
+// four slots are used or only clusters are left -- and counts the internal children; a prefix sum over the frontier gives every
+// internal child its index in the next level (children of one node contiguous, levels one after the other: neighbours in a level are
+// neighbours in space, because the order is inherited from the Morton order of the parents).
+struct WideTree {
+    int32_t *src;        // [n_wide] binary node id of every wide node
+    int32_t *child;      // [4 * n_wide] binary node ids of the slots (-1: empty)
+    int32_t *ref;        // [4 * n_wide] child refs as the traversal reads them
+};
+
+__global__ void k_wide_expand(uint32_t m, uint32_t first, TempTree t, WideTree w, uint64_t *counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int32_t X = w.src[first + i];
+    int32_t ch[4] = {t.c0[X], t.c1[X], -1, -1};
+    int n = 2;
+    while (n < 4) {
+        int best = -1; float best_area = -1.0f;
+        for (int k = 0; k < n; ++k) {
+            if (t.size[ch[k]] <= RT_LEAF_MAX) continue;
+            float a = box_half_area(t.lo[ch[k]], t.hi[ch[k]]);
+            if (a > best_area) { best_area = a; best = k; }
+        }
+        if (best < 0) break;
+        const int32_t e = ch[best];
+        ch[best] = t.c0[e]; ch[n++] = t.c1[e];
+    }
+    uint32_t internal = 0;
+    for (int k = 0; k < 4; ++k) {
+        w.child[4 * (size_t)(first + i) + k] = k < n ? ch[k] : -1;
+        if (k < n && t.size[ch[k]] > RT_LEAF_MAX) internal++;
+    }
+    counts[i] = internal;
+}
+
+__global__ void k_wide_assign(uint32_t m, uint32_t first, uint32_t next_first, TempTree t, WideTree w, const uint64_t *scan, const uint32_t *tri_offset) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t at = next_first + (uint32_t)scan[i];
+    for (int k = 0; k < 4; ++k) {
+        const int32_t c = w.child[4 * (size_t)(first + i) + k];
+        int32_t ref = (int32_t)RT_EMPTY_REF;
+        if (c >= 0) {
+            if (t.size[c] > RT_LEAF_MAX) { w.src[at] = c; ref = (int32_t)at; at++; }
+            else ref = leaf_ref(tri_offset[c], t.size[c]);
+        }
+        w.ref[4 * (size_t)(first + i) + k] = ref;
+    }
+}
+
+RT_DEVICE uint32_t quant_lo(float x, double b, double st) { double g = floor(((double)x - b) / st); return (uint32_t)fmin(fmax(g, 0.0), 32767.0); }
+RT_DEVICE uint32_t quant_hi(float x, double b, double st) { double g = ceil(((double)x - b) / st); return (uint32_t)fmin(fmax(g, 0.0), 32767.0); }
+
+__global__ void k_wide_emit(uint32_t n_wide, TempTree t, WideTree w, Q4Node *out, double qbx, double qby, double qbz, double qsx, double qsy, double qsz) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_wide) return;
+    Q4Node z;
+    for (int k = 0; k < 4; ++k) {
+        const int32_t c = w.child[4 * (size_t)i + k];
+        if (c < 0) { z.c[k] = make_uint4(32767u, 32767u, 32767u, RT_EMPTY_REF); continue; }     // lo = 32767, hi = 0: an inverted box (and the ref says empty)
+        const float4 lo = t.lo[c], hi = t.hi[c];                   // exact vertex extents; lo -> floor, hi -> ceil, in double (as k_emit_nodes)
+        z.c[k] = make_uint4(quant_lo(lo.x, qbx, qsx) | (quant_hi(hi.x, qbx, qsx) << 16), quant_lo(lo.y, qby, qsy) | (quant_hi(hi.y, qby, qsy) << 16),
+                            quant_lo(lo.z, qbz, qsz) | (quant_hi(hi.z, qbz, qsz) << 16), (uint32_t)w.ref[4 * (size_t)i + k]);
+    }
+    out[i] = z;
+}
+
 // ---- 5. gather triangles into cluster order ----------------------------------------------------------
 
 struct GatherInput {

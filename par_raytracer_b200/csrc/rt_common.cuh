@@ -87,6 +87,14 @@ static_assert(sizeof(BNode) == 64, "BNode");
 struct __align__(16) QNode { uint32_t w[8]; };
 static_assert(sizeof(QNode) == 32, "QNode");
 
+// 4-wide quantised form (RT_BOUNDS_QBOX4): up to four child boxes on the same 15-bit grid in 64 bytes = FOUR 16-byte loads per node visit,
+// from the binary tree by collapsing (a node's children are replaced by their own children, largest box first, until four slots are
+// full). Half the dependent node fetches per ray of the binary form -- the latency-bound case once the scene has left L1 / L2.
+//   c[k] = (x lo | hi << 16, y lo | hi << 16, z lo | hi << 16, child ref);  empty slot: ref == RT_EMPTY_REF
+struct __align__(16) Q4Node { uint4 c[4]; };
+static_assert(sizeof(Q4Node) == 64, "Q4Node");
+#define RT_EMPTY_REF 0x80000000u      // == RT_DONE of the traversal: never a node index, never a leaf ref
+
 #ifndef RT_LEAF_MAX
 #define RT_LEAF_MAX 2            // triangles per cluster (leaf): subtrees of <= RT_LEAF_MAX triangles collapse into one cluster (measured 1 / 2 / 3 / 4 / 6: 2 is fastest)
 #endif
@@ -126,6 +134,7 @@ struct DevScene {
     const HNode *nodes;            // sphere + slab child bounds (RT_B200_BOUNDS=sphere)
     const BNode *bnodes;           // axis-aligned child bounds, full floats (RT_B200_BOUNDS=box)
     const QNode *qnodes;           // axis-aligned child bounds on the 15-bit scene grid (default)
+    const Q4Node *q4nodes;         // same grid, four children per node (RT_B200_BOUNDS=qbox4)
     float qmid[3];                 // qbase - 32768 * qstep per axis (the decode offset, see qbox_ray_setup)
     float qstep[3];
     const TriRec *tris;
@@ -158,6 +167,8 @@ struct DevParams {
 #define RT_BOUNDS_SPHERE 0        // child bound of the traversal (rt_trace.cuh): sphere + slab, float boxes, boxes on the 15-bit scene grid
 #define RT_BOUNDS_BOX 1
 #define RT_BOUNDS_QBOX 2
+#define RT_BOUNDS_QBOX4 3
 #define RT_STACK_MAX 64           // traversal stack entries per ray; the build guarantees depth + 2 <= RT_STACK_MAX
+#define RT_STACK4_MAX 96          // 4-wide form: at most 3 pushes per level; the build guarantees 3 * levels + 2 <= RT_STACK4_MAX
 
 #define RT_SEED_MULT 0x9E3779B97F4A7C15ULL

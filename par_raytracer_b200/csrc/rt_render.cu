@@ -37,9 +37,8 @@ static void host_phong_dirs(const std::vector<float> &spec_intensity, uint32_t s
 // persistent-grid sizes: resident blocks of the whole chip for the trace kernel of the selected child bound and for k_logic
 int rt_render_configure(rt_scene *sc) {
     int per_sm = 0;
-    const char *be = getenv("RT_B200_BOUNDS");      // "box" / "sphere": the float-box and sphere + slab child bounds (kept for the comparison in profiles/)
-    sc->bounds = (be && strcmp(be, "sphere") == 0) ? RT_BOUNDS_SPHERE : (be && strcmp(be, "box") == 0) ? RT_BOUNDS_BOX : RT_BOUNDS_QBOX;
-    if (sc->bounds == RT_BOUNDS_QBOX) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_QBOX>, RT_TRACE_BLOCK, 0));
+    if (sc->bounds == RT_BOUNDS_QBOX4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_QBOX4>, RT_TRACE_BLOCK, 0));
+    else if (sc->bounds == RT_BOUNDS_QBOX) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_QBOX>, RT_TRACE_BLOCK, 0));
     else if (sc->bounds == RT_BOUNDS_BOX) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_BOX>, RT_TRACE_BLOCK, 0));
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_wave<false, RT_BOUNDS_SPHERE>, RT_TRACE_BLOCK, 0));
     sc->trace_grid = sc->sm_count * std::max(1, per_sm);
@@ -193,7 +192,8 @@ static int launch_trace_wave(rt_scene *sc, float bias, const WaveQueues &w, cons
     uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)sc->trace_grid, std::max<uint64_t>(1, (work_bound + RT_TRACE_BLOCK - 1) / RT_TRACE_BLOCK));
 #define RT_TRACE_LAUNCH(B) do { if (count) k_trace_wave<true, B><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc); \
                                 else k_trace_wave<false, B><<<grid, RT_TRACE_BLOCK, 0, st>>>(sc->d, bias, w, gen, tc); } while (0)
-    if (sc->bounds == RT_BOUNDS_QBOX) RT_TRACE_LAUNCH(RT_BOUNDS_QBOX);
+    if (sc->bounds == RT_BOUNDS_QBOX4) RT_TRACE_LAUNCH(RT_BOUNDS_QBOX4);
+    else if (sc->bounds == RT_BOUNDS_QBOX) RT_TRACE_LAUNCH(RT_BOUNDS_QBOX);
     else if (sc->bounds == RT_BOUNDS_BOX) RT_TRACE_LAUNCH(RT_BOUNDS_BOX);
     else RT_TRACE_LAUNCH(RT_BOUNDS_SPHERE);
 #undef RT_TRACE_LAUNCH

@@ -204,17 +204,48 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
             qs[a] = (double)sc->d.qstep[a];
         }
     }
-    if (!grid_ok && sc->bounds == RT_BOUNDS_QBOX) sc->bounds = RT_BOUNDS_BOX;   // float boxes need no grid (inf / NaN vertices behave as they do there)
+    if (!grid_ok && (sc->bounds == RT_BOUNDS_QBOX || sc->bounds == RT_BOUNDS_QBOX4)) sc->bounds = RT_BOUNDS_BOX;   // float boxes need no grid (inf / NaN vertices behave as they do there)
     // only the node array of the selected child bound is built (RT_B200_BOUNDS)
-    HNode *nodes = nullptr; BNode *bnodes = nullptr; QNode *qnodes = nullptr;
-    if (sc->bounds == RT_BOUNDS_SPHERE) CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
+    HNode *nodes = nullptr; BNode *bnodes = nullptr; QNode *qnodes = nullptr; Q4Node *q4nodes = nullptr;
+    uint32_t n_wide = 0, wide_levels = 0;
+    if (sc->bounds == RT_BOUNDS_QBOX4 && kept_nodes > 0) {
+        // collapse to four children per node, level by level from the root (kernels + comment in rt_build.cuh)
+        WideTree w;
+        CKB(tmp.alloc(&w.src, kept_nodes)); CKB(tmp.alloc(&w.child, 4 * (size_t)kept_nodes)); CKB(tmp.alloc(&w.ref, 4 * (size_t)kept_nodes));
+        const int32_t root_id = (int32_t)(n_total - 1);
+        CKB(cudaMemcpyAsync(w.src, &root_id, 4, cudaMemcpyHostToDevice, st));
+        uint32_t first = 0, m = 1;
+        while (m > 0) {
+            const uint32_t nb = cdiv(m, SCAN_TILE);
+            k_wide_expand<<<cdiv(m, 128), 128, 0, st>>>(m, first, t, w, flags); CKLB("k_wide_expand");
+            k_scan_reduce<<<nb, SCAN_BLOCK, 0, st>>>(flags, m, bsums); CKLB("k_scan_reduce");
+            k_scan_blocksums<<<1, 1024, 0, st>>>(bsums, nb, total); CKLB("k_scan_blocksums");
+            k_scan_apply<<<nb, SCAN_BLOCK, 0, st>>>(flags, m, bsums, scan); CKLB("k_scan_apply");
+            k_wide_assign<<<cdiv(m, 128), 128, 0, st>>>(m, first, first + m, t, w, scan, tri_offset); CKLB("k_wide_assign");
+            uint64_t h_total = 0;
+            CKB(cudaMemcpyAsync(&h_total, total, 8, cudaMemcpyDeviceToHost, st));
+            CKB(cudaStreamSynchronize(st));
+            first += m; m = (uint32_t)h_total; wide_levels++;
+            if ((uint64_t)first + m > kept_nodes) return done(fail(RT_ERR_STATE, "4-wide collapse produced more nodes than the binary tree has"));
+        }
+        n_wide = first;
+        if (3 * wide_levels + 2 > RT_STACK4_MAX) { sc->bounds = RT_BOUNDS_QBOX; n_wide = 0; }     // too deep for the 4-wide traversal stack: binary form
+        else {
+            CKB(sc->mem.alloc(&q4nodes, std::max(1u, n_wide)));
+            k_wide_emit<<<cdiv(n_wide, 128), 128, 0, st>>>(n_wide, t, w, q4nodes, qb[0], qb[1], qb[2], qs[0], qs[1], qs[2]); CKLB("k_wide_emit");
+        }
+    }
+    if (sc->bounds == RT_BOUNDS_QBOX4 && kept_nodes == 0) sc->bounds = RT_BOUNDS_QBOX;           // a scene of one cluster has no nodes at all
+    if (sc->bounds == RT_BOUNDS_QBOX4) { /* node array emitted above */ }
+    else if (sc->bounds == RT_BOUNDS_SPHERE) CKB(sc->mem.alloc(&nodes, std::max(1u, kept_nodes)));
     else if (sc->bounds == RT_BOUNDS_BOX) CKB(sc->mem.alloc(&bnodes, std::max(1u, kept_nodes)));
     else CKB(sc->mem.alloc(&qnodes, std::max(1u, kept_nodes)));
     if (n > 1) {
         k_slot_to_tri<<<cdiv(n, 256), 256, 0, st>>>(n, vals, tri_offset, slot_tri); CKLB("k_slot_to_tri");
         if (sc->bounds == RT_BOUNDS_SPHERE) { k_refit<<<cdiv((uint64_t)(n - 1) * 32, 256), 256, 0, st>>>(n, n_total, t, tri_offset, slot_tri, bin); CKLB("k_refit"); }
     }
-    if (kept_nodes > 0) {
+    if (kept_nodes > 0 && sc->bounds == RT_BOUNDS_QBOX4) sc->d.root = 0;
+    else if (kept_nodes > 0) {
         k_emit_nodes<<<cdiv(n - 1, 256), 256, 0, st>>>(n, n_total, t, tri_offset, kept_index, nodes, bnodes, qnodes, qb[0], qb[1], qb[2], qs[0], qs[1], qs[2]); CKLB("k_emit_nodes");
         sc->d.root = 0;
     } else {
@@ -228,7 +259,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     CKB(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 
-    sc->d.nodes = nodes; sc->d.bnodes = bnodes; sc->d.qnodes = qnodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
+    sc->d.nodes = nodes; sc->d.bnodes = bnodes; sc->d.qnodes = qnodes; sc->d.q4nodes = q4nodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
     sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object;
     sc->d.n_tris = n; sc->d.n_nodes = kept_nodes;
     {   // every sphere lies inside the root sphere: |c|_1 + r <= |c_root|_1 + sqrt(3) * 2 r_root + r_root
@@ -237,7 +268,9 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
         sc->d.cull_bound = fabsf(rs.x) + fabsf(rs.y) + fabsf(rs.z) + 4.5f * rs.w;
     }
     sc->info[0] = n; sc->info[1] = 0; sc->info[2] = kept_nodes; sc->info[3] = depth;
-    sc->info[4] = (uint64_t)kept_nodes * (sc->bounds == RT_BOUNDS_QBOX ? sizeof(QNode) : sc->bounds == RT_BOUNDS_BOX ? sizeof(BNode) : sizeof(HNode)); sc->info[5] = (uint64_t)n * sizeof(TriRec);
+    sc->info[4] = sc->bounds == RT_BOUNDS_QBOX4 ? (uint64_t)n_wide * sizeof(Q4Node)
+                : (uint64_t)kept_nodes * (sc->bounds == RT_BOUNDS_QBOX ? sizeof(QNode) : sc->bounds == RT_BOUNDS_BOX ? sizeof(BNode) : sizeof(HNode));
+    if (sc->bounds == RT_BOUNDS_QBOX4) { sc->info[1] = n_wide; sc->info[3] = wide_levels; } sc->info[5] = (uint64_t)n * sizeof(TriRec);
     sc->info[6] = (uint64_t)(ms * 1000.0f); sc->info[7] = iterations;
     return done(RT_OK);
 #undef CKB
@@ -306,7 +339,11 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     CKS(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
     CKS(cudaEventCreate(&sc->ev0)); CKS(cudaEventCreate(&sc->ev1));
     CKS(cudaDeviceGetAttribute(&sc->sm_count, cudaDevAttrMultiProcessorCount, device));
-    { int rc_ = rt_render_configure(sc); if (rc_) return bail(rc_); }
+    {   // child bound of the GPU hierarchy; the build may fall back (non-finite extents -> float boxes, over-deep tree -> binary)
+        const char *be = getenv("RT_B200_BOUNDS");
+        sc->bounds = (be && strcmp(be, "sphere") == 0) ? RT_BOUNDS_SPHERE : (be && strcmp(be, "box") == 0) ? RT_BOUNDS_BOX
+                   : (be && strcmp(be, "qbox4") == 0) ? RT_BOUNDS_QBOX4 : RT_BOUNDS_QBOX;
+    }
     cudaStream_t st = sc->stream;
 
     // ---- tie-break ranks: the reference's leaf encounter order (raytracer.cpp:168-172, 208-209) ----
@@ -425,6 +462,7 @@ extern "C" int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene *
     }
     CKS(cudaStreamSynchronize(st));
 #undef CKS
+    { int rc_ = rt_render_configure(sc); if (rc_) return bail(rc_); }       // persistent-grid sizes for the bound the build settled on
     *out_scene = sc;
     return RT_OK;
 }

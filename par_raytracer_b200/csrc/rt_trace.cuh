@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
     bool live = false, exhausted = false;
     uint32_t fetch_min = G.enabled ? W.fetch_min_primary : W.fetch_min;
     RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
-    constexpr bool BOX = BOUNDS == RT_BOUNDS_BOX, QBOX = BOUNDS == RT_BOUNDS_QBOX;
+    constexpr bool BOX = BOUNDS == RT_BOUNDS_BOX, Q4 = BOUNDS == RT_BOUNDS_QBOX4, QBOX = BOUNDS == RT_BOUNDS_QBOX || Q4;
     BoxRay R; R.ix = R.iy = R.iz = R.clx = R.cly = R.clz = R.chx = R.chy = R.chz = 0.0f;
     QRay Q; Q.ax = Q.ay = Q.az = Q.cnx = Q.cny = Q.cnz = Q.cfx = Q.cfy = Q.cfz = 0.0f; Q.snx = Q.sny = Q.snz = 0x7104u;
     float inv_dd = 0.0f, slack = 0.0f;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
     // Traversal stack: the logical top lives in the register `top`, the rest in local memory (stack[0] = sentinel). A pop takes
     // the register and issues the reload of the next entry at once, so the load latency is off the critical path of the descent.
     int cur = RT_DONE, sp = 1, top = RT_DONE;
-    int stack[RT_STACK_MAX];
+    int stack[Q4 ? RT_STACK4_MAX : RT_STACK_MAX];
     stack[0] = RT_DONE;
 
     while (true) {
@@ -265,6 +265,33 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
             while (nm != 0) {
 #pragma unroll
                 for (int u = 0; u < RT_NODE_UNROLL; ++u)             // node visits per warp vote
+                if (Q4) {
+                  if (cur >= 0) {
+                    // four children: all four 16-byte words are requested together; the hit children are ordered by entry distance with a
+                    // 5-exchange network on keys = (entry distance bits & ~3) | slot (distances are >= 0: their bits order like unsigned
+                    // integers; a miss is the largest key), nearest first, the others pushed far to near
+                    const uint4 *np = reinterpret_cast<const uint4 *>(S.q4nodes + cur);
+                    const uint4 A = __ldg(np), B = __ldg(np + 1), C = __ldg(np + 2), D = __ldg(np + 3);
+                    float t0, t1, t2, t3;
+                    const bool h0 = qbox_child(A.x, A.y, A.z, Q, tcull, t0) & (A.w != RT_EMPTY_REF);
+                    const bool h1 = qbox_child(B.x, B.y, B.z, Q, tcull, t1) & (B.w != RT_EMPTY_REF);
+                    const bool h2 = qbox_child(C.x, C.y, C.z, Q, tcull, t2) & (C.w != RT_EMPTY_REF);
+                    const bool h3 = qbox_child(D.x, D.y, D.z, Q, tcull, t3) & (D.w != RT_EMPTY_REF);
+                    if (COUNT) n_sph += 4;
+                    const uint32_t k0 = h0 ? (__float_as_uint(t0) & ~3u) : 0xFFFFFFFFu, k1 = h1 ? ((__float_as_uint(t1) & ~3u) | 1u) : 0xFFFFFFFFu;
+                    const uint32_t k2 = h2 ? ((__float_as_uint(t2) & ~3u) | 2u) : 0xFFFFFFFFu, k3 = h3 ? ((__float_as_uint(t3) & ~3u) | 3u) : 0xFFFFFFFFu;
+                    const uint32_t a = min(k0, k1), b = max(k0, k1), c2 = min(k2, k3), d2 = max(k2, k3);
+                    const uint32_t s0 = min(a, c2), f = max(a, c2), g = min(b, d2), s3 = max(b, d2);
+                    const uint32_t s1 = min(f, g), s2 = max(f, g);
+                    auto pick = [&](uint32_t key) { return (int)((key & 2u) ? ((key & 1u) ? D.w : C.w) : ((key & 1u) ? B.w : A.w)); };
+                    if (s0 != 0xFFFFFFFFu) {
+                        if (s3 != 0xFFFFFFFFu) { stack[sp++] = top; top = pick(s3); }     // 3 pushes per level at most: the build bounds the depth
+                        if (s2 != 0xFFFFFFFFu) { stack[sp++] = top; top = pick(s2); }
+                        if (s1 != 0xFFFFFFFFu) { stack[sp++] = top; top = pick(s1); }
+                        cur = pick(s0);
+                    } else { cur = top; top = stack[--sp]; }
+                  }
+                } else
                 if (cur >= 0) {
                     int2 ch; bool h0, h1; float t0, t1;
                     if (QBOX) {
