@@ -13,8 +13,9 @@
 
 #include "rt_render_shim.hpp"
 
-extern "C" int dropin_render(const char *dir, u32 width, u32 height, float fov, const float *cam_pos, const float *cam_facing,
-                             u32 spp, u64 base_seed, float *out_rgba, unsigned long long *out_rays) {
+// min_spp < max_spp: RenderB200's default mode, the reference's adaptive sampling (main.cpp:308-309: 10 .. 50).
+extern "C" int dropin_render_adaptive(const char *dir, u32 width, u32 height, float fov, const float *cam_pos, const float *cam_facing,
+                                      u32 min_spp, u32 max_spp, u64 base_seed, float *out_rgba, unsigned long long *out_rays) {
     char *argv0[] = { (char *)"ref", nullptr };
     InitParams(1, argv0);                                                        // main.cpp:544
     gParams.image_width = width; gParams.image_height = height; gParams.camera_fov = fov;
@@ -42,10 +43,16 @@ extern "C" int dropin_render(const char *dir, u32 width, u32 height, float fov, 
         scene.objects.push_back(obj);
     }
     rt_counters counters;
-    Framebuffer fb = rt_b200::RenderB200(&cam, &scene, gParams.image_width, gParams.image_height, spp, spp, base_seed, 0, &counters);   // <-> main.cpp:602
+    Framebuffer fb = rt_b200::RenderB200(&cam, &scene, gParams.image_width, gParams.image_height, min_spp, max_spp, base_seed, 0, &counters);   // <-> main.cpp:602
+    rt_b200::RenderB200Shutdown();                                               // the Scene above lives on this stack frame: drop the cached device copy
     if (!fb.pixels) return -2;
     memcpy(out_rgba, fb.pixels, (size_t)width * height * 16);
     if (out_rays) *out_rays = counters.ray_count;
     free(fb.pixels);
     return 0;
+}
+
+extern "C" int dropin_render(const char *dir, u32 width, u32 height, float fov, const float *cam_pos, const float *cam_facing,
+                             u32 spp, u64 base_seed, float *out_rgba, unsigned long long *out_rays) {
+    return dropin_render_adaptive(dir, width, height, fov, cam_pos, cam_facing, spp, spp, base_seed, out_rgba, out_rays);
 }

@@ -436,6 +436,181 @@ def heightfield_scene(cells_x: int = 64, cells_z: int = 64, block: int = 16, siz
     return sd
 
 
+def _grid_patch(origin, du, dv, nu: int, nv: int, uv_scale=(1.0, 1.0), bulge=None):
+    """(nu x nv)-cell planar patch spanned by du, dv from `origin`; front face = cross(du, dv). Optional bulge(u, v) -> offset along
+    the normal (drapery, carved relief). Returns pos, uv, nrm, tris with counter-clockwise winding seen from the front."""
+    origin = np.asarray(origin, np.float64); du = np.asarray(du, np.float64); dv = np.asarray(dv, np.float64)
+    n = np.cross(du, dv); n /= np.linalg.norm(n)
+    j, i = np.meshgrid(np.arange(nv + 1), np.arange(nu + 1), indexing="ij")
+    u, v = i / nu, j / nv
+    pos = origin + u[..., None] * du + v[..., None] * dv
+    nrm = np.broadcast_to(n, pos.shape).copy()
+    if bulge is not None:
+        h = bulge(u, v)
+        pos = pos + h[..., None] * n
+        hu = np.gradient(h, axis=1) * nu / np.linalg.norm(du); hv = np.gradient(h, axis=0) * nv / np.linalg.norm(dv)
+        nrm = n - hu[..., None] * du / np.linalg.norm(du) - hv[..., None] * dv / np.linalg.norm(dv)
+        nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    uv = np.stack([u * uv_scale[0], v * uv_scale[1]], axis=-1)
+    jj, ii = np.meshgrid(np.arange(nv), np.arange(nu), indexing="ij")
+    v00 = (jj * (nu + 1) + ii).reshape(-1); v01 = v00 + 1; v10 = v00 + (nu + 1); v11 = v10 + 1
+    tris = np.empty((2 * len(v00), 3), np.int64)
+    tris[0::2] = np.stack([v00, v01, v11], axis=1)          # cross(du, dv) side is the front
+    tris[1::2] = np.stack([v00, v11, v10], axis=1)
+    return pos.reshape(-1, 3).astype(F32), uv.reshape(-1, 2).astype(F32), nrm.reshape(-1, 3).astype(F32), tris
+
+
+def _cylinder(center, radius: float, y0: float, y1: float, nseg: int, nring: int, flute: float = 0.0):
+    """Column shaft around the y axis through (center.x, center.z), outward facing; `flute` carves shallow grooves."""
+    j, i = np.meshgrid(np.arange(nring + 1), np.arange(nseg + 1), indexing="ij")
+    phi = 2.0 * np.pi * i / nseg
+    r = radius * (1.0 - flute * (0.5 + 0.5 * np.cos(12.0 * phi))) * (1.0 - 0.08 * j / nring)
+    x = center[0] + r * np.cos(phi); z = center[1] + r * np.sin(phi); y = y0 + (y1 - y0) * j / nring
+    pos = np.stack([x, y, z], axis=-1).reshape(-1, 3)
+    nrm = np.stack([np.cos(phi), np.zeros_like(phi), np.sin(phi)], axis=-1).reshape(-1, 3)
+    uv = np.stack([4.0 * i / nseg, 6.0 * j / nring], axis=-1).reshape(-1, 2)
+    jj, ii = np.meshgrid(np.arange(nring), np.arange(nseg), indexing="ij")
+    v00 = (jj * (nseg + 1) + ii).reshape(-1); v01 = v00 + 1; v10 = v00 + (nseg + 1); v11 = v10 + 1
+    tris = np.concatenate([np.stack([v00, v10, v11], axis=1), np.stack([v00, v11, v01], axis=1)], axis=0)
+    order = np.argsort(np.concatenate([np.arange(len(v00)) * 2, np.arange(len(v00)) * 2 + 1]), kind="stable")
+    tris = tris[order]
+    tris = _orient_outward(pos, tris, np.array([center[0], 0.5 * (y0 + y1), center[1]]))
+    # orientation is per triangle about the axis point: good enough for a convex shaft
+    return pos.astype(F32), uv.astype(F32), nrm.astype(F32), tris
+
+
+def sponza_standin_scene(detail: int = 1, name: str = "sponza_standin") -> SceneData:
+    """BASELINE config 1: a procedural stand-in for the Crytek Sponza atrium the reference hard-codes (main.cpp:432, 553; 262,267 triangles,
+    out.txt:1), in Sponza's own coordinate range so that the reference's DEFAULT camera -- position (475, 250, 0), facing (1.25, -0.5, 1.25),
+    fov 60 (main.cpp:426-431) -- looks down the nave: a tiled floor, two storeys of fluted columns, arcade walls with bump-mapped brick, a
+    carved frieze, alpha-masked hanging drapery and foliage, translucent banners, open to the sky (the single directional light comes in
+    from above). ~260 k triangles in ~250 OBJ groups of very different sizes (4 ... 8,192 triangles), 10 materials: diffuse + ambient maps,
+    bump maps, alpha masks, a translucent material. detail = 1 is the full-size scene; smaller values give quick test scenes."""
+    rng = np.random.default_rng(20170218)
+    d = max(0.1, float(detail))
+    q = lambda n: max(2, int(round(n * d)))                 # tessellation counts scale with detail
+    textures = [checker_texture(256, 16, (214, 196, 170), (150, 128, 108), seed=11),      # 0 floor tiles
+                checker_texture(256, 32, (176, 92, 70), (150, 70, 56), seed=12),          # 1 brick
+                bump_texture(256, seed=13),                                                # 2 brick / stone relief
+                mask_texture(256, holes=16),                                               # 3 drapery lace
+                checker_texture(128, 4, (60, 130, 60), (30, 90, 40), seed=14),             # 4 foliage colour
+                mask_texture(128, holes=6),                                                # 5 foliage cut-out
+                bump_texture(128, seed=15)]                                                # 6 column flutes
+    mats = [make_material((0.85, 0.8, 0.72), (0.25, 0.25, 0.25), ns=40.0, diffuse_texture=0, ambient_texture=0),   # 0 floor
+            make_material((0.8, 0.6, 0.5), (0.1, 0.1, 0.1), ns=10.0, diffuse_texture=1, ambient_texture=1, bump_texture=2),   # 1 brick wall
+            make_material((0.78, 0.74, 0.66), (0.3, 0.3, 0.3), ns=40.0, bump_texture=6),      # 2 column stone
+            make_material((0.7, 0.68, 0.62), (0.2, 0.2, 0.2), ns=10.0, bump_texture=2),       # 3 carved frieze
+            make_material((0.75, 0.15, 0.12), (0.2, 0.2, 0.2), ns=10.0, alpha_texture=3),     # 4 red drapery (alpha mask)
+            make_material((0.2, 0.55, 0.2), (0.1, 0.1, 0.1), ns=10.0, diffuse_texture=4, alpha_texture=5),   # 5 foliage
+            make_material((0.2, 0.3, 0.75), (0.6, 0.6, 0.6), ns=200.0, d=0.55),              # 6 translucent banner
+            make_material((0.72, 0.7, 0.68), (0.5, 0.5, 0.5), ns=200.0),                       # 7 polished trim
+            make_material((0.55, 0.38, 0.2), (0.1, 0.1, 0.1), ns=10.0),                        # 8 wood
+            make_material((0.8, 0.78, 0.7), (0.15, 0.15, 0.15), ns=40.0, diffuse_texture=0)]   # 9 upper gallery floor
+    mb = MeshBuilder()
+    X0, X1, Z0, Z1 = -1800.0, 1800.0, -700.0, 700.0          # nave; aisles behind the columns to +-1000
+    ZA = 1000.0
+    H1, H2 = 420.0, 840.0                                      # storey heights
+
+    def add(gname, mat, pos, uv, nrm, tris):
+        mb.add_group(gname, mat, pos, uv, nrm, tris)
+
+    # floor: 12 x 6 slabs, each its own group (coarse: flat), plus the aisles
+    nxs, nzs = 12, 6
+    for ix in range(nxs):
+        for iz in range(nzs):
+            x0 = X0 + (X1 - X0) * ix / nxs; z0 = -ZA + 2 * ZA * iz / nzs
+            add(f"floor_{ix}_{iz}", 0, *_grid_patch((x0, 0.0, z0), (0, 0, 2 * ZA / nzs), ((X1 - X0) / nxs, 0, 0), q(6), q(6), uv_scale=(2.0, 3.0)))
+    # outer walls (bump-mapped brick), two storeys, panels of very different tessellation
+    for side, z, sgn in (("n", -ZA, 1.0), ("s", ZA, -1.0)):
+        for storey, (y0, y1) in enumerate(((0.0, H1), (H1, H2 + 200.0))):
+            for ix in range(10):
+                x0 = X0 + (X1 - X0) * ix / 10; dx = (X1 - X0) / 10
+                n_u = q(10 + 14 * ((ix * 7 + storey) % 3))
+                if sgn > 0:
+                    patch = _grid_patch((x0, y0, z), (dx, 0, 0), (0, y1 - y0, 0), n_u, q(12), uv_scale=(3.0, 3.0),
+                                        bulge=lambda u, v: 6.0 * np.sin(6.28 * 3 * u) * np.sin(6.28 * 2 * v))
+                else:
+                    patch = _grid_patch((x0 + dx, y0, z), (-dx, 0, 0), (0, y1 - y0, 0), n_u, q(12), uv_scale=(3.0, 3.0),
+                                        bulge=lambda u, v: 6.0 * np.sin(6.28 * 3 * u) * np.sin(6.28 * 2 * v))
+                add(f"wall_{side}{storey}_{ix}", 1, *patch)
+    for side, x, sgn in (("w", X0, 1.0), ("e", X1, -1.0)):
+        for iz in range(4):
+            z0 = -ZA + 2 * ZA * iz / 4; dz = 2 * ZA / 4
+            if sgn > 0:
+                patch = _grid_patch((x, 0.0, z0 + dz), (0, 0, -dz), (0, H2 + 200.0, 0), q(24), q(32), uv_scale=(3.0, 6.0),
+                                    bulge=lambda u, v: 10.0 * np.cos(6.28 * 2 * u) * np.sin(3.14 * v))
+            else:
+                patch = _grid_patch((x, 0.0, z0), (0, 0, dz), (0, H2 + 200.0, 0), q(24), q(32), uv_scale=(3.0, 6.0),
+                                    bulge=lambda u, v: 10.0 * np.cos(6.28 * 2 * u) * np.sin(3.14 * v))
+            add(f"wall_{side}_{iz}", 1, *patch)
+    # columns: 2 rows x 12 x 2 storeys, fluted, each with a polished base ring
+    ncol = 12
+    for row, z in enumerate((Z0, Z1)):
+        for ic in range(ncol):
+            x = X0 + (X1 - X0) * (ic + 0.5) / ncol
+            for storey, (y0, y1, rad) in enumerate(((0.0, H1 - 40.0, 55.0), (H1, H2 - 40.0, 42.0))):
+                add(f"column_{row}_{ic}_{storey}", 2, *_cylinder((x, z), rad, y0, y1, q(40), q(24), flute=0.06))
+                add(f"colbase_{row}_{ic}_{storey}", 7, *_cylinder((x, z), rad * 1.35, y0, y0 + 30.0, q(24), 1))
+    # gallery floors above the aisles + lintels over the columns (top faces and nave-facing faces)
+    for row, (za, zb) in enumerate(((-ZA, Z0), (Z1, ZA))):
+        for ix in range(6):
+            x0 = X0 + (X1 - X0) * ix / 6; dx = (X1 - X0) / 6
+            add(f"gallery_{row}_{ix}", 9, *_grid_patch((x0, H1, za), (0, 0, zb - za), (dx, 0, 0), q(4), q(8), uv_scale=(1.0, 2.0)))
+            add(f"gallery_under_{row}_{ix}", 3, *_grid_patch((x0, H1 - 40.0, za), (dx, 0, 0), (0, 0, zb - za), q(16), q(8), uv_scale=(4.0, 2.0),
+                                                               bulge=lambda u, v: 4.0 * np.sin(6.28 * 4 * u) * np.sin(6.28 * 2 * v)))
+    for row, (z, sgn) in enumerate(((Z0, 1.0), (Z1, -1.0))):
+        for storey, y in enumerate((H1 - 40.0, H2 - 40.0)):
+            for ix in range(6):
+                x0 = X0 + (X1 - X0) * ix / 6; dx = (X1 - X0) / 6
+                relief = lambda u, v: 8.0 * np.sin(6.28 * 12 * u) * np.sin(3.14 * v) ** 2          # the carved frieze: finely tessellated
+                if sgn > 0:
+                    patch = _grid_patch((x0, y, z), (dx, 0, 0), (0, 40.0, 0), q(128), q(8), uv_scale=(8.0, 1.0), bulge=relief)
+                else:
+                    patch = _grid_patch((x0 + dx, y, z), (-dx, 0, 0), (0, 40.0, 0), q(128), q(8), uv_scale=(8.0, 1.0), bulge=relief)
+                add(f"frieze_{row}_{storey}_{ix}", 3, *patch)
+    # drapery: alpha-masked, wavy, hanging between upper columns on both sides (facing the nave) -- 8,192 triangles each at detail 1
+    for row, (z, sgn) in enumerate(((Z0 + 30.0, 1.0), (Z1 - 30.0, -1.0))):
+        for k in range(4):
+            x0 = X0 + (X1 - X0) * (2 * k + 2.6) / ncol; dx = (X1 - X0) / ncol * 0.8
+            wave = lambda u, v: 25.0 * np.sin(6.28 * 5 * u + 2.0 * v) * (0.3 + 0.7 * v)
+            if sgn > 0:
+                patch = _grid_patch((x0, H1 + 60.0, z), (dx, 0, 0), (0, 300.0, 0), q(64), q(64), uv_scale=(2.0, 2.0), bulge=wave)
+            else:
+                patch = _grid_patch((x0 + dx, H1 + 60.0, z), (-dx, 0, 0), (0, 300.0, 0), q(64), q(64), uv_scale=(2.0, 2.0), bulge=wave)
+            add(f"drapery_{row}_{k}", 4, *patch)
+    # translucent banners across the nave (two-sided: a front and a back sheet), low tessellation
+    for k in range(3):
+        x = X0 + (X1 - X0) * (k + 1.5) / 5
+        add(f"banner_{k}_a", 6, *_grid_patch((x, H1 + 100.0, -300.0), (0, 0, 600.0), (0, 260.0, 0), q(8), q(6)))
+        add(f"banner_{k}_b", 6, *_grid_patch((x - 2.0, H1 + 100.0, 300.0), (0, 0, -600.0), (0, 260.0, 0), q(8), q(6)))
+    # planters with foliage: a wooden tub (cylinder) + alpha-cut leaf cards (each card two-sided)
+    for k in range(8):
+        x = X0 + (X1 - X0) * (k + 0.5) / 8; z = (-1.0 if k % 2 else 1.0) * 380.0
+        add(f"tub_{k}", 8, *_cylinder((x, z), 45.0, 0.0, 70.0, q(20), q(4)))
+        cards_p, cards_t, cards_n, cards_i = [], [], [], []
+        base = 0
+        for c in range(q(24)):
+            ang = rng.uniform(0, 2 * np.pi); tilt = rng.uniform(0.2, 0.9); ln = rng.uniform(90.0, 160.0)
+            du = np.array([np.cos(ang) * 30.0, 0.0, np.sin(ang) * 30.0])
+            dv = np.array([-np.sin(ang) * ln * tilt, ln, np.cos(ang) * ln * tilt])
+            org = np.array([x, 70.0, z]) - 0.5 * du
+            for flip in (False, True):
+                pp, tt, nn, ii = _grid_patch(org + (du if flip else 0), (-du if flip else du), dv, 2, 4)
+                cards_p.append(pp); cards_t.append(tt); cards_n.append(nn); cards_i.append(ii + base); base += len(pp)
+        add(f"foliage_{k}", 5, np.concatenate(cards_p), np.concatenate(cards_t), np.concatenate(cards_n), np.concatenate(cards_i))
+    # two finely tessellated ornaments (the "lion heads"): bumpy spheres on pedestals at the far end
+    for k, z in enumerate((-250.0, 250.0)):
+        pos, uv, nrm, tris = uv_sphere((X1 - 260.0, 210.0, z), 90.0, q(128), q(64))
+        r = 1.0 + 0.06 * np.sin(9.0 * pos[:, 0] / 90.0) * np.sin(7.0 * pos[:, 1] / 90.0) * np.cos(8.0 * pos[:, 2] / 90.0)
+        ctr = np.array([X1 - 260.0, 210.0, z], F32)
+        pos = (ctr + (pos - ctr) * r[:, None]).astype(F32)
+        add(f"ornament_{k}", 3, pos, uv, nrm, tris)
+        add(f"pedestal_{k}", 7, *_cylinder((X1 - 260.0, z), 70.0, 0.0, 125.0, q(24), q(4)))
+    sd = mb.finish(np.array(mats, dtype=MATERIAL), textures, name=name)
+    sd.camera_hint = dict(position=(475.0, 250.0, 0.0), facing=(1.25, -0.5, 1.25), fov=60.0)      # main.cpp:426-431  # type: ignore[attr-defined]
+    return sd
+
+
 def use_reference_hierarchy(sd: SceneData, device: int = 0) -> SceneData:
     """Replaces sd.spheres / sd.sphere_group by the reference's OWN hierarchy over the mesh groups -- BuildHierarchy
     (bsphere.cpp:379-444) run on the GPU by rt_build_group_hierarchy, bit-identical to the host build (tests/test_gpu_parity.py) --

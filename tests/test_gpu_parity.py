@@ -272,6 +272,7 @@ def test_adaptive_sampling_against_reference(gscene):
     img, cnt = S.render_task(gs.cam, p, gs.W, gs.H, flags=api.RT_FLAG_ADAPTIVE)
     ns = S.sample_counts(gs.W * gs.H)
     same = ns == gs.adaptive_nsamples
+    print(f"adaptive sampling: {int((~same).sum())} of {same.size} pixels stop at a different sample count than the reference")
     assert same.mean() >= 0.995, f"sample counts differ on {(~same).sum()} pixels"
     assert gs.adaptive_nsamples.min() < gs.adaptive_minmax[1], "fixture must exercise the early exit"
     assert np.allclose(img[same], gs.adaptive_rgba[same], rtol=RTOL, atol=ATOL)
@@ -309,6 +310,7 @@ def test_adaptive_chunking_is_invisible(monkeypatch):
     a, ca = S.render_task(cam, p, W, H, flags=api.RT_FLAG_ADAPTIVE)
     na = S.sample_counts(W * H)
     same = na == ns_o
+    print(f"adaptive chunking: {int((~same).sum())} of {same.size} pixels stop at a different sample count than the oracle")
     assert same.mean() >= 0.995, f"sample counts differ on {(~same).sum()} pixels"     # colours agree to ~1e-7: threshold ties may flip
     assert np.allclose(a[same], ref[same], rtol=RTOL, atol=ATOL)
     if same.all():
