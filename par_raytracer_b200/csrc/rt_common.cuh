@@ -26,10 +26,16 @@ RT_DEVICE float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  
 RT_DEVICE f3 cross3(f3 a, f3 b) {                                                // mathlib.h:239-246
     return mk3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
 }
-// IEEE x / l for l > 0. A zero numerator sends CUDA's div.rn into its out-of-line slow path (~35 instructions + call; ncu showed
-// 15 % of k_logic's instructions there: the tangent frames of raytracer.cpp:306-312 always carry an exact 0 component). 0 / l is the
-// numerator itself (sign kept) for every l that is not NaN, so that case is answered without dividing -- same bits.
-RT_DEVICE float div_pos(float x, float l) { return (x == 0.0f && l == l) ? x : x / l; }
+// IEEE x / l for l > 0. A zero numerator sends CUDA's div.rn into its out-of-line slow path (~35 instructions + call): ncu showed 13-18 % of
+// k_logic's executed instructions there, because the tangent frames of raytracer.cpp:306-312 always carry an exact 0 component. A branch
+// around the division does not help -- the compiler if-converts it and the FCHK of the (now speculative) division still calls the slow
+// path -- so the division is given a numerator it can handle (l / l) and the exact answer is selected afterwards: 0 / l is the numerator
+// itself (sign kept) for every l that is not NaN. Same bits, no slow path.
+RT_DEVICE float div_pos(float x, float l) {
+    const bool zero = x == 0.0f;
+    const float q = (zero ? l : x) / l;
+    return (zero && l == l) ? x : q;
+}
 RT_DEVICE f3 normalize3(f3 a) {                                                  // mathlib.h:253-262
     float l2 = dot3(a, a);
     if (l2 == 0.0f) return a;

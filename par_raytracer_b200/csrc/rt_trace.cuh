@@ -173,6 +173,9 @@ RT_DEVICE bool qbox_child(uint32_t wx, uint32_t wy, uint32_t wz, const QRay &Q, 
 #ifndef RT_NODE_UNROLL
 #define RT_NODE_UNROLL 2            // node visits between two warp votes (measured: 2 and 4 are equal, 1 is 3-5 % slower)
 #endif
+#ifndef RT_STACK_TOP_REG
+#define RT_STACK_TOP_REG 1          // 1: the logical stack top lives in a register (a pop is a move, the reload is issued at once)
+#endif
 #define RT_DONE ((int)0x80000000)      // never a leaf ref: |leaf ref| <= 1 + 8 * 2e8 + 7 < 2^31
 
 
@@ -198,9 +201,10 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
     int kind = 0;                  // 0 closest hit -> hits[out_idx]; 1 shadow, boolean; 2 shadow, needs t (point light); shadow kinds carry the light index << 2
     // Traversal stack: the logical top lives in the register `top`, the rest in local memory (stack[0] = sentinel). A pop takes
     // the register and issues the reload of the next entry at once, so the load latency is off the critical path of the descent.
-    int cur = RT_DONE, sp = 1, top = RT_DONE;
+    int cur = RT_DONE, top = RT_DONE;
     int stack[Q4 ? RT_STACK4_MAX : RT_STACK_MAX];
     stack[0] = RT_DONE;
+    int *sptr = stack + 1;         // next free entry
 
     while (true) {
         // ---- warp-cooperative fetch ----
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                     else { c.d = dir; inv_dd = approx_rcp(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, dir.x * dir.x))); }   // culling only
                     best.t = FLT_MAX; best.v = 0.0f; best.w = 0.0f; best.tri = -1; best_rank = 0xFFFFFFFFu;   // raytracer.cpp:166
                     tcull = FLT_MAX;
-                    cur = S.n_tris ? S.root : RT_DONE; sp = 1; top = RT_DONE;
+                    cur = S.n_tris ? S.root : RT_DONE; sptr = stack + 1; top = RT_DONE;
                     live = true;
                 }
             }
@@ -285,11 +289,11 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                     const uint32_t s1 = min(f, g), s2 = max(f, g);
                     auto pick = [&](uint32_t key) { return (int)((key & 2u) ? ((key & 1u) ? D.w : C.w) : ((key & 1u) ? B.w : A.w)); };
                     if (s0 != 0xFFFFFFFFu) {
-                        if (s3 != 0xFFFFFFFFu) { stack[sp++] = top; top = pick(s3); }     // 3 pushes per level at most: the build bounds the depth
-                        if (s2 != 0xFFFFFFFFu) { stack[sp++] = top; top = pick(s2); }
-                        if (s1 != 0xFFFFFFFFu) { stack[sp++] = top; top = pick(s1); }
+                        if (s3 != 0xFFFFFFFFu) { *sptr++ = top; top = pick(s3); }     // 3 pushes per level at most: the build bounds the depth
+                        if (s2 != 0xFFFFFFFFu) { *sptr++ = top; top = pick(s2); }
+                        if (s1 != 0xFFFFFFFFu) { *sptr++ = top; top = pick(s1); }
                         cur = pick(s0);
-                    } else { cur = top; top = stack[--sp]; }
+                    } else { cur = top; top = *--sptr; }
                   }
                 } else
                 if (cur >= 0) {
@@ -316,14 +320,19 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                         h1 = cull_child(s1, p1, m4.y, c.o, c.d, inv_dd, slack, best.t, t1);
                     }
                     if (COUNT) n_sph += 2;
-                    const bool second_first = h1 && (!h0 || t1 < t0);
-                    const int near = second_first ? ch.y : ch.x;
-                    const int far = second_first ? ch.x : ch.y;
-                    if (h0 && h1) {
-                        stack[sp++] = top; top = far;                // depth <= RT_STACK_MAX - 2 is guaranteed by the build
-                    }
-                    if (h0 || h1) cur = near;
-                    else { cur = top; top = stack[--sp]; }
+                    const bool first0 = h0 && (t0 <= t1);            // child 0 is entered first; else child 1 if it is hit at all
+                    const bool swap = h1 && !first0;
+                    const int near = swap ? ch.y : ch.x;
+                    const int far = swap ? ch.x : ch.y;
+                    const bool both = h0 && h1, any = h0 || h1;
+#if RT_STACK_TOP_REG
+                    if (both) { *sptr++ = top; top = far; }          // depth <= RT_STACK_MAX - 2 is guaranteed by the build
+                    cur = any ? near : top;
+                    if (!any) top = *--sptr;
+#else
+                    if (both) *sptr++ = far;
+                    if (any) cur = near; else cur = *--sptr;
+#endif
                 }
                 nm = __ballot_sync(FULL, cur >= 0);
                 if (__popc(nm) < keep) break;
@@ -374,7 +383,11 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
                     }
                 }
                 if ((kind & 3) == 1 && best.tri >= 0) cur = RT_DONE;                     // occlusion only needs TraceRay's bool (raytracer.cpp:385)
-                else { cur = top; top = stack[--sp]; }
+#if RT_STACK_TOP_REG
+                else { cur = top; top = *--sptr; }
+#else
+                else cur = *--sptr;
+#endif
             }
             if (cur == RT_DONE) {
                 if (kind == 0) {
