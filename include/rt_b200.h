@@ -121,7 +121,10 @@ typedef struct rt_stats {
  * base_seed: the per-(pixel,sample) seeding contract. Sample s of
  * linear pixel index p draws from a RandomState seeded with
  *     Random_Seed(base_seed ^ (p * 0x9E3779B97F4A7C15 + s))          (u64 wrap-around)
- * random.h arithmetic unchanged. The oracle harness uses the same contract. */
+ * random.h arithmetic unchanged. The oracle harness uses the same contract.
+ * Limits (RT_ERR_ARG otherwise): bounce_depth <= 200; reflection_samples + spec_samples <= 1e6; and the recursion tree of ONE sample
+ * -- (reflection + spec + 1)^level nodes per level, 1 + reflection_samples draws per node -- must not be able to take more than
+ * 65535 random draws (the per-path draw counter is 16 bits; the defaults take at most 2 + 13 * 2 = 28). */
 typedef struct rt_params {
     float    ray_bias;
     uint32_t reflection_samples;

@@ -396,7 +396,12 @@ __global__ void k_emit_nodes(uint32_t n, uint32_t n_nodes_total, TempTree t, con
     if (bnodes || qnodes) {
         float4 la = t.lo[a], ha = t.hi[a], lb = t.lo[b], hb = t.hi[b];      // exact vertex extents; the traversal pads them per ray
         BNode q;
-        q.a = make_float4(la.x, la.y, la.z, ha.x); q.b = make_float4(ha.y, ha.z, lb.x, lb.y); q.c = make_float4(lb.z, hb.x, hb.y, hb.z);
+        // centre + half-extent per child; the half-extent is rounded UP from the rounded centre so that [c - h, c + h] contains [lo, hi]
+        auto ctr = [](float lo, float hi) { return 0.5f * lo + 0.5f * hi; };
+        auto hext = [](float lo, float hi, float c) { float h = fmaxf(hi - c, c - lo); return h > 0.0f ? __uint_as_float(__float_as_uint(h * 1.0000002f) + 1u) : 0.0f; };
+        const float cax = ctr(la.x, ha.x), cay = ctr(la.y, ha.y), caz = ctr(la.z, ha.z), cbx = ctr(lb.x, hb.x), cby = ctr(lb.y, hb.y), cbz = ctr(lb.z, hb.z);
+        q.a = make_float4(cax, cay, caz, hext(la.x, ha.x, cax)); q.b = make_float4(hext(la.y, ha.y, cay), hext(la.z, ha.z, caz), cbx, cby);
+        q.c = make_float4(cbz, hext(lb.x, hb.x, cbx), hext(lb.y, hb.y, cby), hext(lb.z, hb.z, cbz));
         q.c0 = ref_a; q.c1 = ref_b;
         q.pad0 = q.pad1 = 0;
         if (bnodes) bnodes[kept_index[v]] = q;
@@ -502,7 +507,7 @@ struct GatherInput {
 
 
 __global__ void k_gather(GatherInput in, const uint32_t *sorted_tri, const uint32_t *tri_offset, TriRec *tris, uint32_t *tri_rank,
-                         float4 *tri_uv, float4 *tri_nrm, float4 *tri_tan, uint32_t *tri_vertex0, int32_t *tri_object) {
+                         float4 *tri_uv, float4 *tri_nrm, float4 *tri_tan, uint32_t *tri_vertex0, int32_t *tri_object, uint8_t *tri_mat) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;      // sorted position == temp leaf node id
     if (i >= in.n_tris) return;
     uint32_t j = sorted_tri[i];                               // input triangle
@@ -523,6 +528,7 @@ __global__ void k_gather(GatherInput in, const uint32_t *sorted_tri, const uint3
     tri_rank[dst] = in.group_rank_base[g] + v0 / 3u;
     tri_vertex0[dst] = v0;
     tri_object[dst] = in.group_object[g];
+    tri_mat[dst] = (uint8_t)((uint32_t)in.group_material[g] & 255u);
     const float *t0 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 0];
     const float *t1 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 1];
     const float *t2 = in.texcoords + 2 * (size_t)in.idx_t[3 * (size_t)j + 2];

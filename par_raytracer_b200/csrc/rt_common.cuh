@@ -76,9 +76,9 @@ struct __align__(16) HNode {
 };
 static_assert(sizeof(HNode) == 80, "HNode");
 
-// Box form of the same node (the default traversal bound, see rt_trace.cuh): both children's axis-aligned bounds in the
-// parent, 64 bytes = half a cache line, four 16-byte loads. Same tree, same child refs as HNode.
-//   a = (lo0.x lo0.y lo0.z hi0.x)  b = (hi0.y hi0.z lo1.x lo1.y)  c = (lo1.z hi1.x hi1.y hi1.z)
+// Float-box form of the same node (RT_B200_BOUNDS=box): both children's axis-aligned bounds in the parent as centre + half-extent,
+// 64 bytes = half a cache line, four 16-byte loads. Same tree, same child refs as HNode.
+//   a = (c0.x c0.y c0.z h0.x)  b = (h0.y h0.z c1.x c1.y)  c = (c1.z h1.x h1.y h1.z)
 struct __align__(16) BNode {
     float4 a, b, c;
     int32_t c0, c1;
@@ -148,6 +148,7 @@ struct DevScene {
     const float4 *tri_uv;          // 2 per triangle: (u0 v0 u1 v1) (u2 v2 material_bits -)
     const float4 *tri_nrm;         // 3 per triangle: vertex normals; the three w's hold Normalize(Cross(ab, ac)) (raytracer.cpp:122)
     const float4 *tri_tan;         // 3 per triangle: vertex tangents (NULL when no bump map)
+    const uint8_t *tri_mat;        // material index & 255 per triangle: the sort key of the shading step (grouping only, never a result)
     const uint32_t *tri_vertex0;   // RaycastHit::vertex0 (raytracer.cpp:147)
     const int32_t *tri_object;     // RaycastHit::object as sphere index (raytracer.cpp:148)
     const DevMaterial *materials;  // [n_materials] + default at index n_materials

@@ -122,7 +122,23 @@ static DevParams to_dev_params(const rt_params *p) {
 static int check_params(const rt_params *p) {
     if (!p) return fail(RT_ERR_ARG, "params is null");
     if (p->bounce_depth > 200) return fail(RT_ERR_ARG, "bounce_depth %u > 200", p->bounce_depth);
-    if (p->reflection_samples + p->spec_samples > 1000000u) return fail(RT_ERR_ARG, "too many reflection samples");
+    if ((uint64_t)p->reflection_samples + p->spec_samples > 1000000u) return fail(RT_ERR_ARG, "too many reflection samples");
+    // The per-path draw counter is 16 bits wide (pack_state, rt_shade.cuh). Worst case of one sample: 2 jitter draws, then every node of
+    // the recursion tree (reflection + specular children, + 1 translucent continuation, bounce_depth levels below the root) takes one
+    // Russian-roulette draw and one draw per diffuse child (raytracer.cpp:416-420, 519-520). Reject what could wrap the counter.
+    {
+        const uint64_t fan = (uint64_t)p->reflection_samples + p->spec_samples + 1u, per_node = 1u + (uint64_t)p->reflection_samples;
+        uint64_t nodes = 1, level = 1, draws = 2;
+        bool ok = true;
+        for (uint32_t d = 0; d < p->bounce_depth && ok; ++d) {
+            if (level > 65535u / fan) { ok = false; break; }
+            level *= fan; nodes += level;
+            if (nodes > 65535u) ok = false;
+        }
+        if (ok) { draws += nodes * per_node; if (draws > 65535u) ok = false; }
+        if (!ok) return fail(RT_ERR_ARG, "bounce_depth %u with %u + %u samples per bounce can take more than 65535 random draws per sample (the per-path draw counter is 16 bits)",
+                             p->bounce_depth, p->reflection_samples, p->spec_samples);
+    }
     return RT_OK;
 }
 
@@ -227,7 +243,7 @@ static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint3
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         CK(cudaMemsetAsync(p.counts + (cur ^ 1), 0, 4, st));
         if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
-        k_logic<<<std::min(cdiv(std::max(1u, bound), 128), (uint32_t)sc->logic_grid), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow, gen);
+        k_logic<<<std::min(cdiv(std::max(1u, bound), RT_LOGIC_CHUNK), (uint32_t)sc->logic_grid), 128, 0, st>>>(sc->d, prm, p.paths, p.q[cur], p.hits, p.counts + cur, bound, p.q[cur ^ 1], p.counts + (cur ^ 1), p.shadow, gen);
         CKL("k_logic");
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }

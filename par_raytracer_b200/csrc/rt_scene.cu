@@ -103,9 +103,9 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     CKB(cudaEventRecord(e0, st));
 
     // final arrays
-    TriRec *tris; uint32_t *tri_rank, *tri_vertex0; int32_t *tri_object; float4 *tri_uv, *tri_nrm, *tri_tan = nullptr;
+    TriRec *tris; uint32_t *tri_rank, *tri_vertex0; int32_t *tri_object; float4 *tri_uv, *tri_nrm, *tri_tan = nullptr; uint8_t *tri_mat;
     CKB(sc->mem.alloc(&tris, n)); CKB(sc->mem.alloc(&tri_rank, n)); CKB(sc->mem.alloc(&tri_vertex0, n));
-    CKB(sc->mem.alloc(&tri_object, n)); CKB(sc->mem.alloc(&tri_uv, 2 * (size_t)n)); CKB(sc->mem.alloc(&tri_nrm, 3 * (size_t)n));
+    CKB(sc->mem.alloc(&tri_object, n)); CKB(sc->mem.alloc(&tri_mat, n)); CKB(sc->mem.alloc(&tri_uv, 2 * (size_t)n)); CKB(sc->mem.alloc(&tri_nrm, 3 * (size_t)n));
     if (has_tangents) CKB(sc->mem.alloc(&tri_tan, 3 * (size_t)n));
 
     uint32_t n_pad = BITONIC_TILE;
@@ -251,7 +251,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     } else {
         sc->d.root = -(int)(1u + 0u * 8u + n);     // the whole scene is one cluster (n <= RT_LEAF_MAX)
     }
-    k_gather<<<cdiv(n, 256), 256, 0, st>>>(gin, vals, tri_offset, tris, tri_rank, tri_uv, tri_nrm, tri_tan, tri_vertex0, tri_object);
+    k_gather<<<cdiv(n, 256), 256, 0, st>>>(gin, vals, tri_offset, tris, tri_rank, tri_uv, tri_nrm, tri_tan, tri_vertex0, tri_object, tri_mat);
     CKLB("k_gather");
     CKB(cudaEventRecord(e1, st));
     CKB(cudaStreamSynchronize(st));
@@ -260,7 +260,7 @@ static int build_hierarchy(rt_scene *sc, const BuildInput &bin, const GatherInpu
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 
     sc->d.nodes = nodes; sc->d.bnodes = bnodes; sc->d.qnodes = qnodes; sc->d.q4nodes = q4nodes; sc->d.tris = tris; sc->d.tri_rank = tri_rank; sc->d.tri_uv = tri_uv; sc->d.tri_nrm = tri_nrm;
-    sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object;
+    sc->d.tri_tan = tri_tan; sc->d.tri_vertex0 = tri_vertex0; sc->d.tri_object = tri_object; sc->d.tri_mat = tri_mat;
     sc->d.n_tris = n; sc->d.n_nodes = kept_nodes;
     {   // every sphere lies inside the root sphere: |c|_1 + r <= |c_root|_1 + sqrt(3) * 2 r_root + r_root
         float4 rs;

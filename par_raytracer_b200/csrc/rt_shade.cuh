@@ -151,20 +151,64 @@ RT_DEVICE float phong_pow(float x, float e) { return (x == 0.0f && e > 0.0f) ? 0
 #ifndef RT_LOGIC_MIN_BLOCKS
 #define RT_LOGIC_MIN_BLOCKS 6
 #endif
+#ifndef RT_LOGIC_CHUNK
+#define RT_LOGIC_CHUNK 256       // queue entries a block sorts by material and deals to its 128 threads at a time (multiple of 128, <= 65536; measured 256 / 512 / 1024 / 2048: profiles/README.md)
+#endif
 __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
                                               uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh, PrimaryGen G) {
     const uint32_t n_in = G.enabled ? G.n_slots : min(*n_in_ptr, n_in_max);
     const uint32_t cap = P.capacity;
     const int bd = (int)prm.bounce_depth;
-    // persistent blocks, block-uniform trip count (every lane of a warp reaches the warp-aggregated pushes together); the hit record
-    // of the NEXT trip is requested at the top of the current one (the first, otherwise fully exposed, load of a trip)
-    HitRec h_next; h_next.t = 0.0f; h_next.v = 0.0f; h_next.w = 0.0f; h_next.tri = -1;
-    if (blockIdx.x * blockDim.x + threadIdx.x < n_in) h_next = hits[blockIdx.x * blockDim.x + threadIdx.x];
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n_in; base += gridDim.x * blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    bool active = i < n_in;
-    const HitRec h_cur = h_next;
-    { uint64_t in = (uint64_t)i + (uint64_t)gridDim.x * blockDim.x; if (in < n_in) h_next = hits[in]; }
+    // Persistent blocks, block-uniform trip counts (every lane of a warp reaches the warp-aggregated pushes together). A block takes
+    // RT_LOGIC_CHUNK consecutive queue entries at a time and deals them to its threads SORTED by (miss | material of the hit triangle):
+    // a counting sort of the chunk's hit records in shared memory. Bounce rays of neighbouring queue entries hit unrelated materials or
+    // the sky, and the shading code of a textured / bump-mapped / masked material differs from the plain one's: unsorted, ncu showed 10 of
+    // 32 lanes per instruction (4 in the texture code) on the waves after the first; after the deal a warp mostly holds one kind of work.
+    // The order inside a key is arrival order -- irrelevant: paths are independent, and every path owns its slot.
+    __shared__ HitRec s_hit[RT_LOGIC_CHUNK];
+    __shared__ uint16_t s_perm[RT_LOGIC_CHUNK];
+    __shared__ uint32_t s_bin[64];
+    for (uint32_t chunk = blockIdx.x * RT_LOGIC_CHUNK; chunk < n_in; chunk += gridDim.x * RT_LOGIC_CHUNK) {
+    const uint32_t n_chunk = min((uint32_t)RT_LOGIC_CHUNK, n_in - chunk);
+    {
+        constexpr int PER = RT_LOGIC_CHUNK / 128;
+        uint32_t my_key[PER], my_rank[PER];
+        if (threadIdx.x < 64) s_bin[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const uint32_t e = threadIdx.x + 128u * j;
+            my_key[j] = 0; my_rank[j] = 0;
+            if (e < n_chunk) {
+                const HitRec h = hits[chunk + e];
+                s_hit[e] = h;
+                my_key[j] = h.tri < 0 ? 0u : 1u + (uint32_t)(__ldg(S.tri_mat + h.tri) % 63u);
+                my_rank[j] = atomicAdd(&s_bin[my_key[j]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {              // exclusive prefix over the 64 bins
+            const uint32_t a = s_bin[2 * threadIdx.x], b = s_bin[2 * threadIdx.x + 1];
+            uint32_t incl = a + b;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += v; }
+            s_bin[2 * threadIdx.x] = incl - a - b; s_bin[2 * threadIdx.x + 1] = incl - b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const uint32_t e = threadIdx.x + 128u * j;
+            if (e < n_chunk) s_perm[s_bin[my_key[j]] + my_rank[j]] = (uint16_t)e;
+        }
+        __syncthreads();
+    }
+    for (uint32_t trip = 0; trip < RT_LOGIC_CHUNK; trip += 128) {
+    if (trip >= n_chunk) break;                     // block-uniform
+    const uint32_t pidx = trip + threadIdx.x;
+    const bool active = pidx < n_chunk;
+    const uint32_t e_local = active ? (uint32_t)s_perm[pidx] : 0u;
+    const uint32_t i = chunk + e_local;
+    HitRec h_cur; h_cur.t = 0.0f; h_cur.v = 0.0f; h_cur.w = 0.0f; h_cur.tri = -1;
+    if (active) h_cur = s_hit[e_local];
 
     uint32_t slot = 0, sp = 0;
     int iters = 0;
@@ -385,6 +429,8 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
         }
     }
     if (emit) { qout.o[pos] = mk4(e_org, 0.0f); qout.d[pos] = mk4u(e_dir, slot); }
+    }
+    __syncthreads();                                // the next chunk reuses the shared arrays
     }
 }
 

@@ -89,23 +89,29 @@ RT_DEVICE bool tri_test(const TriRec &r, const RayCtx &c, float &t_out, float &v
 // fattened hi plane (hi + slack - o) i = hi i - (o - slack) i, whatever the sign of d: one FMA per plane against two per-ray
 // constants per axis, so the padding is free. |d| is clamped away from zero (1e-20: the fake drift over any t is far below
 // the slack) so that no 0 * inf appears. FMA / approximate reciprocal are allowed: the result only prunes.
-struct BoxRay { float ix, iy, iz, clx, cly, clz, chx, chy, chz; };
+struct BoxRay { float ix, iy, iz, ax, ay, az, cnx, cny, cnz, cfx, cfy, cfz; };
 
 RT_DEVICE float safe_rcp(float d) { return approx_rcp(fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d); }
 
+// Centre / half-extent form of the float box: the parameter interval of the fattened slab of axis a is
+//     [ (c - o) i - (h + slack) |i| ,  (c - o) i + (h + slack) |i| ],   i = 1 / d,
+// whatever the sign of d -- no near / far selection, no per-axis min / max: four FMAs per axis against per-ray constants
+// (cn = -o i - slack |i|, cf = -o i + slack |i|), all on the FMA pipe. The ALU pipe (min / max, compares, byte permutes), which bounds
+// the quantised form, only sees the two 3-input min / max pairs and the compare.
 RT_DEVICE void box_ray_setup(BoxRay &R, f3 o, f3 d, float slack) {
     R.ix = safe_rcp(d.x); R.iy = safe_rcp(d.y); R.iz = safe_rcp(d.z);
-    R.clx = -(o.x + slack) * R.ix; R.chx = -(o.x - slack) * R.ix;
-    R.cly = -(o.y + slack) * R.iy; R.chy = -(o.y - slack) * R.iy;
-    R.clz = -(o.z + slack) * R.iz; R.chz = -(o.z - slack) * R.iz;
+    R.ax = fabsf(R.ix); R.ay = fabsf(R.iy); R.az = fabsf(R.iz);
+    R.cnx = __fmaf_rn(-slack, R.ax, -o.x * R.ix); R.cfx = __fmaf_rn(slack, R.ax, -o.x * R.ix);
+    R.cny = __fmaf_rn(-slack, R.ay, -o.y * R.iy); R.cfy = __fmaf_rn(slack, R.ay, -o.y * R.iy);
+    R.cnz = __fmaf_rn(-slack, R.az, -o.z * R.iz); R.cfz = __fmaf_rn(slack, R.az, -o.z * R.iz);
 }
 
-RT_DEVICE bool box_child(float lx, float ly, float lz, float hx, float hy, float hz, const BoxRay &R, float tmax, float &tn) {
-    float tlx = __fmaf_rn(lx, R.ix, R.clx), thx = __fmaf_rn(hx, R.ix, R.chx);
-    float tly = __fmaf_rn(ly, R.iy, R.cly), thy = __fmaf_rn(hy, R.iy, R.chy);
-    float tlz = __fmaf_rn(lz, R.iz, R.clz), thz = __fmaf_rn(hz, R.iz, R.chz);
-    tn = fmaxf(fmaxf(fminf(tlx, thx), fminf(tly, thy)), fmaxf(fminf(tlz, thz), 0.0f));       // FMNMX3 pairs on sm_100a
-    float tf = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fminf(fmaxf(tlz, thz), tmax));
+RT_DEVICE bool box_child(float cx, float cy, float cz, float hx, float hy, float hz, const BoxRay &R, float tmax, float &tn) {
+    float tnx = __fmaf_rn(-hx, R.ax, __fmaf_rn(cx, R.ix, R.cnx)), tfx = __fmaf_rn(hx, R.ax, __fmaf_rn(cx, R.ix, R.cfx));
+    float tny = __fmaf_rn(-hy, R.ay, __fmaf_rn(cy, R.iy, R.cny)), tfy = __fmaf_rn(hy, R.ay, __fmaf_rn(cy, R.iy, R.cfy));
+    float tnz = __fmaf_rn(-hz, R.az, __fmaf_rn(cz, R.iz, R.cnz)), tfz = __fmaf_rn(hz, R.az, __fmaf_rn(cz, R.iz, R.cfz));
+    tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));       // FMNMX3 pairs on sm_100a
+    float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
     return tn <= tf;
 }
 
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(RT_TRACE_BLOCK, RT_TRACE_MIN_BLOCKS) k_trace_w
     uint32_t fetch_min = G.enabled ? W.fetch_min_primary : W.fetch_min;
     RayCtx c; c.o = mk3(0, 0, 0); c.d = c.o; c.qp = c.o;
     constexpr bool BOX = BOUNDS == RT_BOUNDS_BOX, Q4 = BOUNDS == RT_BOUNDS_QBOX4, QBOX = BOUNDS == RT_BOUNDS_QBOX || Q4;
-    BoxRay R; R.ix = R.iy = R.iz = R.clx = R.cly = R.clz = R.chx = R.chy = R.chz = 0.0f;
+    BoxRay R; R.ix = R.iy = R.iz = R.ax = R.ay = R.az = R.cnx = R.cny = R.cnz = R.cfx = R.cfy = R.cfz = 0.0f;
     QRay Q; Q.ax = Q.ay = Q.az = Q.cnx = Q.cny = Q.cnz = Q.cfx = Q.cfy = Q.cfz = 0.0f; Q.snx = Q.sny = Q.snz = 0x7104u;
     float inv_dd = 0.0f, slack = 0.0f;
     HitRec best; best.t = FLT_MAX; best.v = 0; best.w = 0; best.tri = -1;

@@ -50,3 +50,24 @@ def test_combined_adaptive_and_argument_errors(golden_scene):
     with pytest.raises(api.RtError):
         api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, root=3)
     comm.close(); S.close()
+
+
+def test_render_is_ordered_after_the_callers_default_stream(golden_scene):
+    """rt_render_device with stream handle 0 (torch's default stream is the legacy stream) must wait for work already enqueued there: a
+    long chain of writes that poison the output frame is queued on the default stream right before the call; if the render did not wait
+    for it, the poison would land after (or in the middle of) the render's own output."""
+    import torch
+    gs = golden_scene
+    S = api.Scene(gs.scene)
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
+    want, _ = S.render(gs.cam, p, gs.W, gs.H)
+    frame = torch.zeros((gs.W * gs.H, 4), dtype=torch.float32, device="cuda")
+    big = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for rep in range(3):
+        for _ in range(20):
+            big.zero_()                                   # ~1 ms of queued work on the default (legacy) stream ...
+        frame.fill_(float("nan"))                         # ... that ends by poisoning the frame
+        S.render_device(gs.cam, p, gs.W, gs.H, frame.data_ptr(), flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME, stream=0)
+        got = frame.cpu().numpy()                         # default-stream copy: ordered after the render (the library makes the stream wait)
+        assert np.array_equal(got.view(np.uint32), want.reshape(-1, 4).view(np.uint32)), f"repetition {rep}: the render overtook the caller's stream"
+    S.close()
