@@ -17,8 +17,9 @@ pageable host framebuffer out) with the same flags. `also` carries the same meas
 and config 4 (10 M triangles, 3840x2160, 256 spp) taken in the same process.
 
 N > 1 (torchrun, one rank per GPU): STRONG scaling of the same frame -- interleaved 32x32 tiles per rank (the reference's pixel split,
-main.cpp:311-319, made interleaved: NOTES.txt:25), one rt_render_combined call per rank and step: render + ncclReduce(SUM) of the float4
-frames to rank 0 on the render stream (replaces MPI_Gather, main.cpp:345-347) inside the library. `combine_parity`: untimed check that
+main.cpp:311-319, made interleaved: NOTES.txt:25), one rt_render_combined call per rank and step: render + the gather of the float4 frames on
+rank 0 (replaces MPI_Gather, main.cpp:345-347) inside the library -- peer-memory stores into rank 0's frame over NVLink where CUDA IPC maps it,
+else ncclReduce(SUM) on the render stream. `combine_parity`: untimed check that
 rank 0's combined frame is bit-identical to its own single-GPU render of the whole frame.
 
 --impl reference: times the reference's own CPU implementation (oracle/_ref = the unmodified reference compiled in the authoring
@@ -272,7 +273,7 @@ def run_reference(args, rank, world):
     r = arm.measure(budget_s=budget, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"],
-            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[key][3], "note": "CPU reference path: the unmodified reference on the host cores renders a bounded pixel subset of the same frame; the metric is a rate"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -392,6 +393,13 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
         return None
 
     peak, peak_src = measured_peak_gbs()
+    if world == 1:
+        combine_desc = "none"
+    elif ctx.comm.stats()["peer_memory"]:
+        combine_desc = ("rt_render_combined, inside the timed region: every rank's resolve kernel stores its tiles straight into rank 0's %d MB frame over NVLink "
+                        "(CUDA IPC peer memory: no zero-fill, no reduce of frames); one ncclReduce of the 24-byte counters is the completion signal" % (n_px * 16 >> 20))
+    else:
+        combine_desc = "rt_render_combined, inside the timed region: ncclReduce(SUM) of the %d MB float4 frames to rank 0 on the render stream" % (n_px * 16 >> 20)
     bpr = b_ray(n_tris)
     ms, e_ms = dev_run["ms"], e2e_run["ms"]
     value = rays / (ms * 1e-3) / 1e6
@@ -404,7 +412,7 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
         "value": value, "ms_per_step": ms / steps,
         "config": {"workload": desc, "width": W, "height": H, "spp_total": int(params["max_samples"]) if adaptive else spp,
                    "partition": mode, "tile": TILE if mode == "tiles" else None,
-                   "combine": ("rt_render_combined: ncclReduce(SUM) of the %d MB float4 frames to rank 0 on the render stream, inside the timed region" % (n_px * 16 >> 20)) if world > 1 else "none",
+                   "combine": combine_desc,
                    "l2": "256 MB memset flushes L2 before every step; per-step path-state streams (tens of GB) exceed the 126 MB L2",
                    "hierarchy": "reference BuildHierarchy over the mesh groups (rt_build_group_hierarchy, bit-identical) for the tie-break order; traversal on the GPU-built cluster hierarchy",
                    "triangles": n_tris, "hierarchy_nodes": info["nodes"], "scene_generate_s": gen_s, "scene_create_s": scene_create_s,
@@ -470,7 +478,7 @@ def run_ours(args, rank, world, local_rank):
             c = CpuArm(key, sd, cam, params).measure(budget_s=15.0)
             cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line = {"metric": METRIC, "value": head["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+                "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",      # the same frame at every N
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
         for k in ("config", "clocks", "e2e", "gpu_launches", "roofline"):
             line[k] = head[k]

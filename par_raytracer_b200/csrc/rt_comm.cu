@@ -25,6 +25,8 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
     std::string why;
@@ -41,6 +43,7 @@ static NcclApi *nccl_api() {
 #define RT_SYM(field, name) do { *(void **)(&api.field) = dlsym(h, name); if (!api.field) { api.why = "symbol " name " missing in libnccl"; return; } } while (0)
         RT_SYM(GetUniqueId, "ncclGetUniqueId"); RT_SYM(CommInitRank, "ncclCommInitRank"); RT_SYM(CommInitAll, "ncclCommInitAll");
         RT_SYM(CommDestroy, "ncclCommDestroy"); RT_SYM(Reduce, "ncclReduce"); RT_SYM(GetErrorString, "ncclGetErrorString");
+        RT_SYM(Broadcast, "ncclBroadcast"); RT_SYM(AllReduce, "ncclAllReduce");
 #undef RT_SYM
         api.ok = true;
     });
@@ -71,6 +74,13 @@ struct rt_comm {
     float4 *frame = nullptr; size_t frame_cap = 0;          // W*H float4, grow-only
     uint8_t *rgba8 = nullptr; size_t rgba8_cap = 0;
     unsigned long long *d_cnt = nullptr;                    // 3 counters staged for their reduce
+    // multi-process peer memory (CUDA IPC): the root's frame mapped into this rank's address space
+    unsigned char *d_ipc = nullptr;                         // 64-byte cudaIpcMemHandle_t + 8 bytes of status, staged for the broadcast
+    float4 *ipc_own = nullptr; size_t ipc_own_cap = 0;      // root: the exported frame (its own allocation: never reallocated behind the peers' backs)
+    float4 *ipc_frame = nullptr;                            // root's exported frame as this rank sees it (root: == ipc_own)
+    float4 *last_frame = nullptr;                           // where the last combined frame lives (rt_comm_frame)
+    size_t ipc_px = 0; int ipc_root = -1;                   // what the mapping covers
+    bool ipc_off = false;                                   // the ranks agreed that IPC does not work here (threads of one process, different nodes, ...)
     std::vector<uint32_t> tile_ids; uint32_t tile_w = 0, tile_h = 0, tile_sz = 0;     // cached tile partition
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     double stats[4] = {0, 0, 0, 0};
@@ -81,6 +91,8 @@ static int comm_alloc(rt_comm **out, int n, int rank, int device) {
     rt_comm *c = new rt_comm;
     c->n = n; c->rank = rank; c->device = device;
     cudaError_t e = cudaMalloc((void **)&c->d_cnt, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_ipc, 128);
+    if (getenv("RT_B200_NO_IPC")) c->ipc_off = true;
     if (e == cudaSuccess) e = cudaEventCreate(&c->e0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->e1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->e2);
@@ -177,8 +189,11 @@ extern "C" void rt_comm_destroy(rt_comm *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->nccl && nccl_api()->ok) nccl_api()->CommDestroy(c->nccl);
+    if (c->ipc_frame && c->ipc_frame != c->ipc_own) cudaIpcCloseMemHandle(c->ipc_frame);
+    if (c->ipc_own) cudaFree(c->ipc_own);
     if (c->frame) cudaFree(c->frame);
     if (c->rgba8) cudaFree(c->rgba8);
+    if (c->d_ipc) cudaFree(c->d_ipc);
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->e0) cudaEventDestroy(c->e0);
     if (c->e1) cudaEventDestroy(c->e1);
@@ -194,7 +209,7 @@ extern "C" void rt_comm_destroy(rt_comm *c) {
 
 extern "C" int rt_comm_rank(const rt_comm *c) { return c ? c->rank : -1; }
 extern "C" int rt_comm_size(const rt_comm *c) { return c ? c->n : 0; }
-extern "C" const float *rt_comm_frame(const rt_comm *c) { return c ? (const float *)c->frame : nullptr; }
+extern "C" const float *rt_comm_frame(const rt_comm *c) { return c ? (const float *)c->last_frame : nullptr; }
 extern "C" int rt_comm_get_stats(const rt_comm *c, double out[4]) {
     if (!c || !out) return fail(RT_ERR_ARG, "null argument");
     memcpy(out, c->stats, sizeof(c->stats));
@@ -309,23 +324,83 @@ static int render_share(rt_scene *scene, rt_comm *comm, const rt_camera *cam, co
 }
 
 // root only: optional tone map + downloads of the finished frame
-static int deliver(rt_scene *scene, rt_comm *comm, uint32_t width, uint32_t height, float *out_rgba_host, uint8_t *out_rgba8_host, float *out_scene_luma) {
+static int deliver(rt_scene *scene, rt_comm *comm, const float4 *frame, uint32_t width, uint32_t height, float *out_rgba_host, uint8_t *out_rgba8_host,
+                   float *out_scene_luma) {
     const size_t n_px = (size_t)width * height;
     cudaStream_t st = scene->stream;
     CK(cudaEventRecord(comm->e1, st));
     if (out_rgba8_host || out_scene_luma) {
         int rc = grow_dev(&comm->rgba8, &comm->rgba8_cap, n_px * 4);
         if (rc) return rc;
-        rc = rt_tonemap_device(comm->device, (const float *)comm->frame, width, height, comm->rgba8, out_scene_luma, st);
+        rc = rt_tonemap_device(comm->device, (const float *)frame, width, height, comm->rgba8, out_scene_luma, st);
         if (rc) return rc;
         if (out_rgba8_host) { CK(cudaMemcpyAsync(out_rgba8_host, comm->rgba8, n_px * 4, cudaMemcpyDeviceToHost, st)); scene->stats.d2h_bytes += n_px * 4; }
     }
-    if (out_rgba_host) { CK(cudaMemcpyAsync(out_rgba_host, comm->frame, n_px * 16, cudaMemcpyDeviceToHost, st)); scene->stats.d2h_bytes += n_px * 16; }
+    if (out_rgba_host) { CK(cudaMemcpyAsync(out_rgba_host, frame, n_px * 16, cudaMemcpyDeviceToHost, st)); scene->stats.d2h_bytes += n_px * 16; }
     CK(cudaEventRecord(comm->e2, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, comm->e1, comm->e2));
     comm->stats[1] = ms;
+    return RT_OK;
+}
+
+// Multi-process peer memory: every rank maps the ROOT's frame (CUDA IPC) and its resolve kernel stores its pixels straight into it over
+// NVLink -- the pixel partitions cover the frame, so there is neither a zero-fill nor a reduce of full frames. Collective; returns with
+// comm->ipc_frame set on every rank, or with comm->ipc_off set on every rank (the ranks agree through an all-reduce) when the mapping is
+// not possible (ranks that are threads of one process, ranks on different nodes, IPC disabled): then the NCCL reduce is used.
+static int ensure_ipc(rt_comm *comm, int root, size_t n_px, cudaStream_t st) {
+    if (comm->ipc_off) return RT_OK;
+    if (comm->ipc_frame && comm->ipc_root == root && comm->ipc_px >= n_px) return RT_OK;      // same decision on every rank: same arguments
+    NcclApi *N = nccl_api();
+    const bool is_root = comm->rank == root;
+    if (comm->ipc_frame && comm->ipc_frame != comm->ipc_own) cudaIpcCloseMemHandle(comm->ipc_frame);     // before the root frees what it maps
+    comm->ipc_frame = nullptr; comm->ipc_px = 0; comm->ipc_root = -1;
+    int *d_flag = reinterpret_cast<int *>(comm->d_ipc + 80);
+    {   // barrier: the root may reallocate its exported frame only after every rank has closed its mapping of the old one
+        int one = 1;
+        CK(cudaMemcpyAsync(d_flag, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+        CKN(N->AllReduce(d_flag, d_flag, 1, ncclInt32, ncclMin, comm->nccl, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    unsigned char hbuf[72];
+    memset(hbuf, 0, sizeof(hbuf));
+    if (is_root) {
+        int rc = grow_dev(&comm->ipc_own, &comm->ipc_own_cap, n_px);
+        if (rc) return rc;
+        cudaIpcMemHandle_t h;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+        const cudaError_t e = cudaIpcGetMemHandle(&h, comm->ipc_own);
+        if (e == cudaSuccess) { memcpy(hbuf, &h, 64); hbuf[64] = 1; } else (void)cudaGetLastError();
+        CK(cudaMemcpyAsync(comm->d_ipc, hbuf, 72, cudaMemcpyHostToDevice, st));
+    }
+    CKN(N->Broadcast(comm->d_ipc, comm->d_ipc, 72, ncclUint8, root, comm->nccl, st));
+    CK(cudaMemcpyAsync(hbuf, comm->d_ipc, 72, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int ok = hbuf[64] == 1;
+    float4 *mapped = nullptr;
+    if (ok) {
+        if (is_root) mapped = comm->ipc_own;
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, hbuf, 64);
+            void *ptr = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { ok = 0; (void)cudaGetLastError(); } else mapped = (float4 *)ptr;
+        }
+    }
+    // agree: all or nothing
+    CK(cudaMemcpyAsync(d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    CKN(N->AllReduce(d_flag, d_flag, 1, ncclInt32, ncclMin, comm->nccl, st));
+    int all = 0;
+    CK(cudaMemcpyAsync(&all, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!all) {
+        if (mapped && !is_root) cudaIpcCloseMemHandle(mapped);
+        comm->ipc_off = true;
+        return RT_OK;
+    }
+    comm->ipc_frame = mapped; comm->ipc_px = n_px; comm->ipc_root = root;
     return RT_OK;
 }
 
@@ -339,24 +414,40 @@ extern "C" int rt_render_combined(rt_scene *scene, rt_comm *comm, const rt_camer
     if (comm->n > 1 && !comm->nccl) return fail(RT_ERR_STATE, "this rt_comm has no NCCL communicator (peer-memory group: use rt_render_multi)");
     CK(cudaSetDevice(comm->device));
     const uint32_t n_px = width * height;
-    rc = grow_dev(&comm->frame, &comm->frame_cap, (size_t)n_px);
-    if (rc) return rc;
     cudaStream_t st = scene->stream;
     const bool is_root = comm->rank == root;
     memset(comm->stats, 0, sizeof(comm->stats));
 
-    // pixel partitions: the other ranks' pixels must read as 0 for the sum to equal the gather
-    if (comm->n > 1 || partition != RT_PART_SAMPLES) CK(cudaMemsetAsync(comm->frame, 0, (size_t)n_px * sizeof(float4), st));
+    // Pixel partitions between processes that share NVLink: peer-memory stores into the root's frame (ensure_ipc). One tiny broadcast
+    // from the root FIRST: the root enqueues it only after it has consumed (downloaded / tone-mapped) the previous frame, and every other
+    // rank's stores of this frame are ordered after it on its stream -- nobody overwrites a frame the root is still reading.
+    bool ipc = false;
+    if (comm->n > 1 && partition != RT_PART_SAMPLES && !comm->ipc_off) {
+        rc = ensure_ipc(comm, root, (size_t)n_px, st);
+        if (rc) return rc;
+        ipc = !comm->ipc_off && comm->ipc_frame != nullptr;
+        if (ipc) CKN(nccl_api()->Broadcast(comm->d_ipc + 96, comm->d_ipc + 96, 4, ncclUint8, root, comm->nccl, st));
+    }
+    if (!ipc) { rc = grow_dev(&comm->frame, &comm->frame_cap, (size_t)n_px); if (rc) return rc; }
+    float4 *const frame = ipc ? comm->ipc_frame : comm->frame;      // where this rank's pixels go; on the root: the combined frame
+    comm->last_frame = frame;
+    // NCCL reduce of pixel partitions: the other ranks' pixels must read as 0 for the sum to equal the gather
+    if (!ipc && (comm->n > 1 || partition != RT_PART_SAMPLES)) CK(cudaMemsetAsync(frame, 0, (size_t)n_px * sizeof(float4), st));
     rt_counters cnt;
     memset(&cnt, 0, sizeof(cnt));
-    rc = render_share(scene, comm, cam, params, width, height, partition, tile, flags, comm->frame, &cnt);
+    rc = render_share(scene, comm, cam, params, width, height, partition, tile, flags, frame, &cnt);
     if (rc) return rc;
     const rt_stats render_stats = scene->stats;
 
     CK(cudaEventRecord(comm->e0, st));
     if (comm->n > 1) {
         NcclApi *N = nccl_api();
-        CKN(N->Reduce(comm->frame, comm->frame, (size_t)n_px * 4, ncclFloat, ncclSum, root, comm->nccl, st));
+        if (!ipc) {
+            CKN(N->Reduce(frame, frame, (size_t)n_px * 4, ncclFloat, ncclSum, root, comm->nccl, st));
+            comm->stats[2] = (double)n_px * 16.0;
+        } else comm->stats[3] = 1.0;
+        // the counters' reduce doubles as the completion signal of the peer-memory gather: it finishes on the root only after every rank has
+        // enqueued it, i.e. after every rank's resolve kernel (and its stores into the root's frame) has completed
         unsigned long long hc[3] = {cnt.ray_count, cnt.sphere_check_count, cnt.mesh_check_count};
         CK(cudaMemcpyAsync(comm->d_cnt, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
         CKN(N->Reduce(comm->d_cnt, comm->d_cnt, 3, ncclUint64, ncclSum, root, comm->nccl, st));
@@ -365,16 +456,15 @@ extern "C" int rt_render_combined(rt_scene *scene, rt_comm *comm, const rt_camer
             CK(cudaStreamSynchronize(st));
             cnt.ray_count = hc[0]; cnt.sphere_check_count = hc[1]; cnt.mesh_check_count = hc[2];
         }
-        comm->stats[2] = (double)n_px * 16.0;
     }
     if (partition == RT_PART_SAMPLES && is_root) {
-        k_samples_resolve<<<cdiv(n_px, 256), 256, 0, st>>>(comm->frame, n_px, (float)params->min_samples);
+        k_samples_resolve<<<cdiv(n_px, 256), 256, 0, st>>>(frame, n_px, (float)params->min_samples);
         CKL("k_samples_resolve");
         scene->stats.kernel_launches += 1;
     }
     CK(cudaEventRecord(comm->e1, st));
     if (is_root && (out_rgba_host || out_rgba8_host || out_scene_luma)) {
-        rc = deliver(scene, comm, width, height, out_rgba_host, out_rgba8_host, out_scene_luma);
+        rc = deliver(scene, comm, frame, width, height, out_rgba_host, out_rgba8_host, out_scene_luma);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(st));
@@ -426,6 +516,7 @@ extern "C" int rt_render_multi(rt_scene *const *scenes, rt_comm *const *comms, i
     CK(cudaSetDevice(root->device));
     { int rc = grow_dev(&root->frame, &root->frame_cap, (size_t)n_px); if (rc) return rc; }
     memset(root->stats, 0, sizeof(root->stats));
+    root->last_frame = root->frame;
     const bool samples = partition == RT_PART_SAMPLES;
     if (samples) for (int i = 1; i < n; ++i) { CK(cudaSetDevice(comms[i]->device)); int rc = grow_dev(&comms[i]->frame, &comms[i]->frame_cap, (size_t)n_px); if (rc) return rc; }
     {
@@ -455,7 +546,7 @@ extern "C" int rt_render_multi(rt_scene *const *scenes, rt_comm *const *comms, i
     CK(cudaEventRecord(root->e1, st));
     root->stats[3] = 1.0;
     if (out_rgba_host || out_rgba8_host || out_scene_luma) {
-        int rc = deliver(scenes[0], root, width, height, out_rgba_host, out_rgba8_host, out_scene_luma);
+        int rc = deliver(scenes[0], root, root->frame, width, height, out_rgba_host, out_rgba8_host, out_scene_luma);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(st));

@@ -1,5 +1,6 @@
-"""NCCL combine on real GPUs (needs >= 2 devices; the driver's single-GPU run skips it, `gpurun --gpus 2` runs it):
-one process per GPU, tiles / ranges / sample ranges, rank 0's frame against the single-GPU render."""
+"""The multi-GPU combine on real GPUs (needs >= 2 devices; the driver's single-GPU run skips it, `gpurun --gpus 2` runs it):
+one process per GPU (rt_render_combined: peer-memory stores through CUDA IPC, or the NCCL reduce of full frames) and one process for
+all GPUs (rt_render_multi), tiles / ranges / sample ranges, rank 0's frame against the single-GPU render."""
 import os
 import sys
 
@@ -11,7 +12,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, mode, out_path):
+def _worker(rank, world, port, mode, out_path, ipc=True):
+    if not ipc:
+        os.environ["RT_B200_NO_IPC"] = "1"           # force the NCCL reduce of full frames
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist_t
@@ -26,6 +29,10 @@ def _worker(rank, world, port, mode, out_path):
     p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
     comm = dist.make_comm(rank, rank, world)
     frame, cnt, _ = dist.render_distributed(S, comm, gs.cam, p, gs.W, gs.H, mode=mode, tile=8)
+    frame2, cnt2, _ = dist.render_distributed(S, comm, gs.cam, p, gs.W, gs.H, mode=mode, tile=8)       # a second frame into the same buffers
+    if rank == 0:
+        assert np.array_equal(frame.view(np.uint32), frame2.view(np.uint32)) and int(cnt["ray_count"]) == int(cnt2["ray_count"])
+        assert comm.stats()["peer_memory"] == (ipc and mode != "samples"), comm.stats()
     if rank == 0:
         np.save(out_path, frame.reshape(-1, 4))
         np.save(out_path + ".rays.npy", np.array([int(cnt["ray_count"])]))      # rt_render_combined sums the counters on the root
@@ -35,14 +42,15 @@ def _worker(rank, world, port, mode, out_path):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 @pytest.mark.parametrize("mode", ["tiles", "ranges", "samples"])
-def test_nccl_combine_equals_single_gpu(tmp_path, mode):
+@pytest.mark.parametrize("ipc", [True, False])
+def test_nccl_combine_equals_single_gpu(tmp_path, mode, ipc):
     import torch.multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import GoldenScene
     gs = GoldenScene("spheres")
     out = str(tmp_path / "frame.npy")
     world = 2
-    mp.spawn(_worker, args=(world, 29700 + (os.getpid() % 1000) + {"tiles": 0, "ranges": 1, "samples": 2}[mode], mode, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29700 + (os.getpid() % 1000) + {"tiles": 0, "ranges": 1, "samples": 2}[mode] + (3 if ipc else 0), mode, out, ipc), nprocs=world, join=True)
     frame = np.load(out)
     rays = int(np.load(out + ".rays.npy")[0])
     want = gs.render_rgba
