@@ -44,7 +44,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mrays/s (primary+secondary)"
 DEFAULT_WORKLOAD = "config3"
-TILE = 32
+TILE = int(os.environ.get("RT_BENCH_TILE", "32"))      # interleaved tile edge of the N > 1 partition (measured 8 / 16 / 32 / 64 at N = 8: profiles/README.md)
 
 # key -> (width, height, spp, description)
 WORKLOADS = {
