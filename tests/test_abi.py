@@ -65,6 +65,35 @@ def test_error_paths_without_compute(lib):
             api.rng_kat(1, 4)
 
 
+def test_multi_gpu_entry_points_fail_loudly_without_compute(lib):
+    """The combine layer's argument checks are host code; without a device every constructor must refuse (no CPU fallback)."""
+    h = C.c_void_p()
+    assert lib.rt_device_count() >= 0
+    assert lib.rt_comm_create(0, 0, None, 0, C.byref(h)) == -1                      # RT_ERR_ARG: 0 ranks
+    assert lib.rt_comm_create(2, 5, (C.c_uint8 * 128)(), 0, C.byref(h)) == -1      # rank out of range
+    assert lib.rt_render_combined(None, None, None, None, 4, 4, 0, 32, 0, 0, None, None, None, None) == -1
+    assert lib.rt_render_multi(None, None, 0, None, None, 4, 4, 0, 32, 0, None, None, None, None) == -1
+    assert lib.rt_comm_rank(None) == -1 and lib.rt_comm_size(None) == 0
+    n = C.c_uint32(0)
+    assert lib.rt_partition_tiles(64, 64, 32, 0, 2, None, C.byref(n)) == 0 and n.value == 2 * 32 * 32      # host-only: works anywhere
+    assert lib.rt_partition_tiles(64, 64, 0, 0, 2, None, C.byref(n)) == -1
+    if not HAS_GPU:
+        assert lib.rt_device_count() == 0
+        assert lib.rt_comm_create(1, 0, None, 0, C.byref(h)) == -2                  # RT_ERR_CUDA: no device
+        assert b"no CPU fallback" in lib.rt_last_error()
+        hs = (C.c_void_p * 1)()
+        assert lib.rt_comm_create_local(1, None, hs) == -2
+    # draw-counter bound of rt_params (host check): the defaults pass, a recursion tree that could take > 65535 draws is refused up front
+    p = types.default_params(spp=1)
+    p["bounce_depth"] = 12; p["reflection_samples"] = 4; p["spec_samples"] = 4
+    sd = scenes.spheres_plane_scene(grid=1, nu=8, nv=4)
+    if HAS_GPU:
+        S = api.Scene(sd)
+        with pytest.raises(api.RtError, match="65535"):
+            S.render(types.make_camera(60.0, 4, 4, (0, 3, 8), (0, -0.3, -1)), p, 4, 4)
+        S.close()
+
+
 def test_product_does_not_import_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
     pkg = os.path.join(ROOT, "par_raytracer_b200")
