@@ -14,6 +14,9 @@
 #include "rt_render_shim.hpp"
 
 // min_spp < max_spp: RenderB200's default mode, the reference's adaptive sampling (main.cpp:308-309: 10 .. 50).
+static int g_dropin_device = 0;      // -1: RenderB200's default -- a single rank drives EVERY GPU of the node (rt_render_multi)
+extern "C" void dropin_set_device(int device) { g_dropin_device = device; }
+
 extern "C" int dropin_render_adaptive(const char *dir, u32 width, u32 height, float fov, const float *cam_pos, const float *cam_facing,
                                       u32 min_spp, u32 max_spp, u64 base_seed, float *out_rgba, unsigned long long *out_rays) {
     char *argv0[] = { (char *)"ref", nullptr };
@@ -43,7 +46,7 @@ extern "C" int dropin_render_adaptive(const char *dir, u32 width, u32 height, fl
         scene.objects.push_back(obj);
     }
     rt_counters counters;
-    Framebuffer fb = rt_b200::RenderB200(&cam, &scene, gParams.image_width, gParams.image_height, min_spp, max_spp, base_seed, 0, &counters);   // <-> main.cpp:602
+    Framebuffer fb = rt_b200::RenderB200(&cam, &scene, gParams.image_width, gParams.image_height, min_spp, max_spp, base_seed, g_dropin_device, &counters);   // <-> main.cpp:602
     rt_b200::RenderB200Shutdown();                                               // the Scene above lives on this stack frame: drop the cached device copy
     if (!fb.pixels) return -2;
     memcpy(out_rgba, fb.pixels, (size_t)width * height * 16);

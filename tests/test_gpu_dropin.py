@@ -93,3 +93,30 @@ def test_config1_reference_defaults_full_size():
     if n_diff == 0:
         assert int(cnt_sub["ray_count"]) == int(cnt_ref["ray_count"])
     S.close()
+
+
+@pytest.mark.skipif(not (os.path.exists(DROPIN) and ref_harness.available()), reason="oracle/_ref not built (needs /root/reference)")
+def test_renderb200_drives_every_gpu_of_the_node():
+    """RenderB200 with its default device (-1) and a single MPI rank: every GPU of the node renders interleaved tiles and the frame is
+    gathered through peer memory (rt_render_multi). The frame must equal the one-GPU frame bit for bit (needs >= 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sd = scenes.spheres_plane_scene(grid=2, nu=20, nv=10, textured=True)
+    d = tempfile.mkdtemp(prefix="dropin_multi_")
+    scenes.write_obj(sd, d)
+    W, H, spp = 160, 96, 4
+    hint = sd.camera_hint
+    pos = np.asarray(hint["position"], np.float32); fac = np.asarray(hint["facing"], np.float32)
+    lib = C.CDLL(DROPIN)
+    frames = []
+    for device in (0, -1):
+        lib.dropin_set_device(C.c_int(device))
+        out = np.zeros((W * H, 4), np.float32); rays = C.c_ulonglong(0)
+        rc = lib.dropin_render(d.encode(), C.c_uint32(W), C.c_uint32(H), C.c_float(hint["fov"]), pos.ctypes.data_as(C.c_void_p),
+                               fac.ctypes.data_as(C.c_void_p), C.c_uint32(spp), C.c_uint64(types.DEFAULT_BASE_SEED), out.ctypes.data_as(C.c_void_p), C.byref(rays))
+        assert rc == 0
+        frames.append((out, rays.value))
+    lib.dropin_set_device(C.c_int(0))
+    assert frames[0][1] == frames[1][1]
+    assert np.array_equal(frames[0][0].view(np.uint32), frames[1][0].view(np.uint32))
