@@ -81,7 +81,8 @@ struct rt_comm {
     float4 *last_frame = nullptr;                           // where the last combined frame lives (rt_comm_frame)
     size_t ipc_px = 0; int ipc_root = -1;                   // what the mapping covers
     bool ipc_off = false;                                   // the ranks agreed that IPC does not work here (threads of one process, different nodes, ...)
-    std::vector<uint32_t> tile_ids; uint32_t tile_w = 0, tile_h = 0, tile_sz = 0;     // cached tile partition
+    std::vector<uint32_t> tile_ids; uint32_t tile_w = 0, tile_h = 0, tile_sz = 0;     // cached tile partition ...
+    uint32_t *d_tile_ids = nullptr; size_t d_tile_cap = 0;                            // ... and its device copy (uploaded once, not per frame)
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     double stats[4] = {0, 0, 0, 0};
 };
@@ -194,6 +195,7 @@ extern "C" void rt_comm_destroy(rt_comm *c) {
     if (c->frame) cudaFree(c->frame);
     if (c->rgba8) cudaFree(c->rgba8);
     if (c->d_ipc) cudaFree(c->d_ipc);
+    if (c->d_tile_ids) cudaFree(c->d_tile_ids);
     if (c->d_cnt) cudaFree(c->d_cnt);
     if (c->e0) cudaEventDestroy(c->e0);
     if (c->e1) cudaEventDestroy(c->e1);
@@ -317,10 +319,13 @@ static int render_share(rt_scene *scene, rt_comm *comm, const rt_camera *cam, co
         comm->tile_ids.resize(count);
         rc = rt_partition_tiles(width, height, tile, comm->rank, comm->n, comm->tile_ids.data(), &count);
         if (rc) return rc;
+        rc = grow_dev(&comm->d_tile_ids, &comm->d_tile_cap, (size_t)count);
+        if (rc) return rc;
+        CK(cudaMemcpy(comm->d_tile_ids, comm->tile_ids.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
         comm->tile_w = width; comm->tile_h = height; comm->tile_sz = tile;
     }
-    return rt_render_device(scene, cam, params, width, height, comm->tile_ids.data(), 0, (uint32_t)comm->tile_ids.size(), 0, params->min_samples,
-                            flags | RT_OUT_MEAN | RT_OUT_FULLFRAME, (float *)dst, nullptr, cnt);
+    return rt_render_device_ids(scene, cam, params, width, height, comm->d_tile_ids, (uint32_t)comm->tile_ids.size(), 0, params->min_samples,
+                                flags | RT_OUT_MEAN | RT_OUT_FULLFRAME, (float *)dst, cnt);
 }
 
 // root only: optional tone map + downloads of the finished frame

@@ -111,3 +111,6 @@ struct rt_scene {
 bool rt_place_quant_grid(double lo, double hi, float *step_out, float *mid_out, double *base_out);
 // rt_render.cu: persistent-grid sizes of the trace / shading kernels for this scene's child bound
 int rt_render_configure(rt_scene *sc);
+// rt_render.cu: rt_render_device with a device-resident, pre-validated pixel list (the cached tile partition of rt_comm.cu)
+int rt_render_device_ids(rt_scene *scene, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height, const uint32_t *pixel_ids_device,
+                         uint32_t pixel_count, uint32_t sample_begin, uint32_t sample_count, uint32_t flags, float *out_rgba_device, rt_counters *out_counters);

@@ -292,16 +292,19 @@ static DevCamera to_dev_camera(const rt_camera *c) {
     return d;
 }
 
+// ids_on_device: pixel_ids is a DEVICE pointer to a list that was validated when it was built (rt_comm's cached tile partition): no
+// per-frame check and no per-frame upload of the list.
 static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height,
                        const uint32_t *pixel_ids, uint32_t pixel_begin, uint32_t pixel_count, uint32_t sample_begin,
-                       uint32_t sample_count, uint32_t flags, float *out_dev, cudaStream_t user_stream, rt_counters *out_counters) {
+                       uint32_t sample_count, uint32_t flags, float *out_dev, cudaStream_t user_stream, rt_counters *out_counters,
+                       bool ids_on_device = false) {
     if (!sc || !cam || !out_dev) return fail(RT_ERR_ARG, "null argument");
     int rc = check_params(params);
     if (rc) return rc;
     if (!width || !height) return fail(RT_ERR_ARG, "empty frame");
     const uint64_t frame = (uint64_t)width * height;
     if (!pixel_ids && (uint64_t)pixel_begin + pixel_count > frame) return fail(RT_ERR_ARG, "pixel range exceeds the frame");
-    if (pixel_ids) for (uint32_t k = 0; k < pixel_count; ++k) if (pixel_ids[k] >= frame) return fail(RT_ERR_ARG, "pixel id %u out of range", pixel_ids[k]);
+    if (pixel_ids && !ids_on_device) for (uint32_t k = 0; k < pixel_count; ++k) if (pixel_ids[k] >= frame) return fail(RT_ERR_ARG, "pixel id %u out of range", pixel_ids[k]);
     CK(cudaSetDevice(sc->device));
     cudaStream_t st = sc->stream;
     // Order after the caller's stream. Handle 0 is the LEGACY default stream (what torch's default stream is): the scene stream is
@@ -343,7 +346,8 @@ static int render_impl(rt_scene *sc, const rt_camera *cam, const rt_params *para
     if (rc) return done(rc);
     float4 *accum = sc->accum;
     CKR(cudaMemsetAsync(accum, 0, (size_t)pixel_count * sizeof(float4), st));
-    if (pixel_ids) {
+    if (pixel_ids && ids_on_device) d_ids = const_cast<uint32_t *>(pixel_ids);
+    else if (pixel_ids) {
         rc = grow(sc, &sc->ids, &sc->ids_cap, pixel_count);
         if (rc) return done(rc);
         d_ids = sc->ids;
@@ -462,6 +466,14 @@ extern "C" int rt_render_device(rt_scene *scene, const rt_camera *cam, const rt_
     g_err.clear();
     return render_impl(scene, cam, params, width, height, pixel_ids, pixel_begin, pixel_count, sample_begin, sample_count, flags,
                        out_rgba_device, (cudaStream_t)stream, out_counters);
+}
+
+// library-internal (rt_comm.cu): rt_render_device with a device-resident, pre-validated pixel list
+int rt_render_device_ids(rt_scene *scene, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height, const uint32_t *pixel_ids_device,
+                         uint32_t pixel_count, uint32_t sample_begin, uint32_t sample_count, uint32_t flags, float *out_rgba_device, rt_counters *out_counters) {
+    g_err.clear();
+    return render_impl(scene, cam, params, width, height, pixel_ids_device, 0, pixel_count, sample_begin, sample_count, flags, out_rgba_device, nullptr,
+                       out_counters, true);
 }
 
 extern "C" int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params *params, uint32_t width, uint32_t height,
