@@ -98,6 +98,7 @@ struct rt_scene {
     float4 *scratch = nullptr; size_t scratch_cap = 0;        // adaptive sampling: per-pixel sample colours
     uint32_t *ad_u32 = nullptr; size_t ad_u32_cap = 0;        // adaptive sampling: nsamples + 2 x (pixel, local) lists + counter
     uint32_t last_adaptive_pixels = 0;
+    uint32_t pool_limit_cached = 0;      // path slots the per-render pool may grow to (decided at the first render from the free device memory)
     std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
     size_t tev_used = 0;
     std::vector<std::pair<uint64_t, uint64_t>> wave_log;   // (closest, shadow) rays per issued wave, aligned with tev (RT_B200_WAVE_LOG=1)
