@@ -311,7 +311,7 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
     n_px = W * H
     base_flags = api.RT_FLAG_TIME_KERNELS | (api.RT_FLAG_ADAPTIVE if adaptive else 0)
     frame = torch.zeros((n_px, 4), dtype=torch.float32, device=dev) if world == 1 else None
-    host_frame = np.empty((n_px, 4), np.float32)                     # pageable host memory, what a C host hands to rt_render
+    host_frame = np.empty((n_px, 4), np.float32)                     # plain host memory, what a C host hands to rt_render
     cam_h = np.asarray(cam).reshape(1).copy(); par_h = np.asarray(params).reshape(1).copy()
 
     def sync_all():
@@ -324,13 +324,13 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
         ctx.flush.zero_()                     # > L2; the render is ordered after it (legacy-stream wait inside the library)
         if world == 1:
             if e2e:
-                _, cnt = S.render_task(cam_h[0], par_h[0], W, H, 0, n_px, flags=api.RT_OUT_MEAN | base_flags, out=host_frame)
+                _, cnt = S.render_task(cam_h[0], par_h[0], W, H, 0, n_px, flags=api.RT_OUT_MEAN | base_flags | api.RT_FLAG_PIN_HOST, out=host_frame)
                 float(host_frame[0, 0])       # the caller reads the result
             else:
                 cnt = S.render_device(cam, params, W, H, frame.data_ptr(), flags=api.RT_OUT_MEAN | api.RT_OUT_FULLFRAME | base_flags, stream=0)
             cst = None
         else:
-            out, _, _, cnt = api.render_combined(S, ctx.comm, cam_h[0], par_h[0], W, H, partition=partition, tile=TILE, flags=base_flags, root=0,
+            out, _, _, cnt = api.render_combined(S, ctx.comm, cam_h[0], par_h[0], W, H, partition=partition, tile=TILE, flags=base_flags | (api.RT_FLAG_PIN_HOST if e2e else 0), root=0,
                                                  want_frame=e2e, out=host_frame if (e2e and rank == 0) else None)
             if e2e and rank == 0:
                 float(host_frame[0, 0])
@@ -421,8 +421,8 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
                    "steps": steps, "warmup": warmup},
         "e2e": {"value": e_rays / (e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e_ms / steps,
                 "h2d_bytes_per_step": int(cam_h.nbytes + par_h.nbytes), "d2h_bytes_per_step": int(n_px * 16),
-                "note": ("rt_render: host camera / params in, pageable host framebuffer out, same flags as `value`" if world == 1 else
-                         "rt_render_combined with the finished frame downloaded to rank 0's pageable host buffer every step") +
+                "note": ("rt_render: host camera / params in, the caller's host framebuffer out (a plain malloc'ed buffer the library page-locks on first sight, RT_FLAG_PIN_HOST), same flags as `value`" if world == 1 else
+                         "rt_render_combined with the finished frame downloaded to rank 0's host buffer every step (page-locked by the library on first sight, RT_FLAG_PIN_HOST)") +
                         "; the scene stays resident like the reference's loaded Scene"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

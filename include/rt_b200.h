@@ -187,6 +187,10 @@ typedef struct rt_scene rt_scene;           /* opaque device-resident scene + GP
 #define RT_OUT_FULLFRAME   2u               /* device output is a W*H frame; pixel p is written at p, others untouched */
 #define RT_FLAG_COUNTERS   4u               /* also count sphere / cluster tests (slower) */
 #define RT_FLAG_TIME_KERNELS 8u             /* CUDA-event-time the trace kernels (adds events, no syncs) */
+#define RT_FLAG_PIN_HOST   32u              /* rt_render / rt_render_combined / rt_render_multi: page-lock the caller's output buffer (cudaHostRegister) the
+                                               first time it is seen and keep it registered while the same pointer comes back, so the download is one
+                                               DMA at PCIe speed instead of a staged pageable copy. The buffer must stay allocated until the scene / comm
+                                               is destroyed or a different buffer is passed. Falls back silently if the registration fails */
 #define RT_FLAG_ADAPTIVE   16u              /* RenderPixel's adaptive second loop (main.cpp:245-258): min_samples fixed samples, then up to
                                                max_samples with the variance test; sample_count is ignored */
 

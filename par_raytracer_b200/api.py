@@ -23,7 +23,7 @@ from .types import CAMERA, COUNTERS, HIT, PARAMS, RAY, STATS, SceneData
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 
-RT_OUT_MEAN, RT_OUT_SUM, RT_OUT_FULLFRAME, RT_FLAG_COUNTERS, RT_FLAG_TIME_KERNELS, RT_FLAG_ADAPTIVE = 0, 1, 2, 4, 8, 16
+RT_OUT_MEAN, RT_OUT_SUM, RT_OUT_FULLFRAME, RT_FLAG_COUNTERS, RT_FLAG_TIME_KERNELS, RT_FLAG_ADAPTIVE, RT_FLAG_PIN_HOST = 0, 1, 2, 4, 8, 16, 32
 RT_TRACE_CLOSEST, RT_TRACE_ANY, RT_TRACE_BRUTE = 0, 1, 2
 
 EXPORTS = ["rt_scene_create", "rt_scene_destroy", "rt_last_error", "rt_abi_version", "rt_render", "rt_render_device",

@@ -84,6 +84,7 @@ struct rt_comm {
     std::vector<uint32_t> tile_ids; uint32_t tile_w = 0, tile_h = 0, tile_sz = 0;     // cached tile partition ...
     uint32_t *d_tile_ids = nullptr; size_t d_tile_cap = 0;                            // ... and its device copy (uploaded once, not per frame)
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    PinnedHost pinned_out;                                  // the caller's float frame (RT_FLAG_PIN_HOST)
     double stats[4] = {0, 0, 0, 0};
 };
 
@@ -189,6 +190,7 @@ extern "C" int rt_comm_create_local(int n, const int *devices, rt_comm **out_com
 extern "C" void rt_comm_destroy(rt_comm *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    c->pinned_out.release();
     if (c->nccl && nccl_api()->ok) nccl_api()->CommDestroy(c->nccl);
     if (c->ipc_frame && c->ipc_frame != c->ipc_own) cudaIpcCloseMemHandle(c->ipc_frame);
     if (c->ipc_own) cudaFree(c->ipc_own);
@@ -293,7 +295,7 @@ static int check_combined_args(rt_scene *scene, rt_comm *comm, const rt_camera *
     if (partition == RT_PART_TILES && !tile) return fail(RT_ERR_ARG, "tile size 0");
     if (partition == RT_PART_SAMPLES && (flags & RT_FLAG_ADAPTIVE) && params->min_samples < params->max_samples)
         return fail(RT_ERR_ARG, "adaptive sampling decides per pixel: use a pixel partition");
-    if (flags & ~(uint32_t)(RT_FLAG_ADAPTIVE | RT_FLAG_TIME_KERNELS | RT_FLAG_COUNTERS)) return fail(RT_ERR_ARG, "flags 0x%x not accepted here", flags);
+    if (flags & ~(uint32_t)(RT_FLAG_ADAPTIVE | RT_FLAG_TIME_KERNELS | RT_FLAG_COUNTERS | RT_FLAG_PIN_HOST)) return fail(RT_ERR_ARG, "flags 0x%x not accepted here", flags);
     return RT_OK;
 }
 
@@ -418,6 +420,8 @@ extern "C" int rt_render_combined(rt_scene *scene, rt_comm *comm, const rt_camer
     if (root < 0 || root >= comm->n) return fail(RT_ERR_ARG, "root %d of %d ranks", root, comm->n);
     if (comm->n > 1 && !comm->nccl) return fail(RT_ERR_STATE, "this rt_comm has no NCCL communicator (peer-memory group: use rt_render_multi)");
     CK(cudaSetDevice(comm->device));
+    if ((flags & RT_FLAG_PIN_HOST) && out_rgba_host && comm->rank == root) comm->pinned_out.pin(out_rgba_host, (size_t)width * height * 16);
+    flags &= ~(uint32_t)RT_FLAG_PIN_HOST;
     const uint32_t n_px = width * height;
     cudaStream_t st = scene->stream;
     const bool is_root = comm->rank == root;
@@ -494,6 +498,8 @@ extern "C" int rt_render_multi(rt_scene *const *scenes, rt_comm *const *comms, i
         if (comms[i]->n != n || comms[i]->rank != i || !comms[i]->group || comms[i]->group != comms[0]->group)
             return fail(RT_ERR_ARG, "comms[%d] is not rank %d of one rt_comm_create_local group of %d", i, i, n);
     }
+    if ((flags & RT_FLAG_PIN_HOST) && out_rgba_host) { CK(cudaSetDevice(comms[0]->device)); comms[0]->pinned_out.pin(out_rgba_host, (size_t)width * height * 16); }
+    flags &= ~(uint32_t)RT_FLAG_PIN_HOST;
     LocalGroup *g = comms[0]->group;
     const bool peer = g->peer_ok || n == 1;
     const uint32_t n_px = width * height;

@@ -44,6 +44,17 @@ static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b -
 // ---------------------------------------------------------------------------------------------
 // device buffer bookkeeping
 // ---------------------------------------------------------------------------------------------
+// A caller's host buffer kept page-locked between calls (RT_FLAG_PIN_HOST)
+struct PinnedHost {
+    void *ptr = nullptr; size_t bytes = 0;
+    void release() { if (ptr) { cudaHostUnregister(ptr); (void)cudaGetLastError(); ptr = nullptr; bytes = 0; } }
+    void pin(void *p, size_t n) {
+        if (p == ptr && n <= bytes) return;
+        release();
+        if (cudaHostRegister(p, n, cudaHostRegisterDefault) == cudaSuccess) { ptr = p; bytes = n; } else (void)cudaGetLastError();
+    }
+};
+
 struct DevArena {
     std::vector<void *> ptrs;
     template <typename T> cudaError_t alloc(T **p, size_t n) {
@@ -98,6 +109,7 @@ struct rt_scene {
     float4 *scratch = nullptr; size_t scratch_cap = 0;        // adaptive sampling: per-pixel sample colours
     uint32_t *ad_u32 = nullptr; size_t ad_u32_cap = 0;        // adaptive sampling: nsamples + 2 x (pixel, local) lists + counter
     uint32_t last_adaptive_pixels = 0;
+    PinnedHost pinned_out;               // rt_render's output buffer (RT_FLAG_PIN_HOST)
     uint32_t pool_limit_cached = 0;      // path slots the per-render pool may grow to (decided at the first render from the free device memory)
     std::vector<cudaEvent_t> tev;        // per-wave kernel timing (RT_FLAG_TIME_KERNELS): 4 events per wave
     size_t tev_used = 0;

@@ -500,6 +500,8 @@ extern "C" int rt_render(rt_scene *scene, const rt_camera *cam, const rt_params 
     if (!scene || !out_rgba_host) return fail(RT_ERR_ARG, "null argument");
     if (flags & RT_OUT_FULLFRAME) return fail(RT_ERR_ARG, "RT_OUT_FULLFRAME is a device-output mode");
     CK(cudaSetDevice(scene->device));
+    if ((flags & RT_FLAG_PIN_HOST) && pixel_count) scene->pinned_out.pin(out_rgba_host, (size_t)pixel_count * 16);
+    flags &= ~(uint32_t)RT_FLAG_PIN_HOST;
     int rc = grow(scene, &scene->out_stage, &scene->out_stage_cap, (size_t)pixel_count * 4);
     if (rc) return rc;
     float *d_out = scene->out_stage;

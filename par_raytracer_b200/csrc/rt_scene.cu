@@ -291,6 +291,7 @@ extern "C" void rt_scene_destroy(rt_scene *sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
     if (sc->stream) cudaStreamSynchronize(sc->stream);
+    sc->pinned_out.release();
     sc->pool.mem.release();
     if (sc->accum) cudaFree(sc->accum);
     if (sc->ids) cudaFree(sc->ids);

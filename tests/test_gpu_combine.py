@@ -71,3 +71,23 @@ def test_render_is_ordered_after_the_callers_default_stream(golden_scene):
         got = frame.cpu().numpy()                         # default-stream copy: ordered after the render (the library makes the stream wait)
         assert np.array_equal(got.view(np.uint32), want.reshape(-1, 4).view(np.uint32)), f"repetition {rep}: the render overtook the caller's stream"
     S.close()
+
+
+def test_pinned_output_buffer_gives_the_same_frame(golden_scene):
+    """RT_FLAG_PIN_HOST page-locks the caller's buffer for the download; the frame is the same, a second buffer replaces the first
+    registration, and a buffer that cannot be registered (a read-only mapping would be one; here: an unaligned view) still works."""
+    gs = golden_scene
+    S = api.Scene(gs.scene)
+    p = gs.params.copy(); p["min_samples"] = p["max_samples"] = gs.render_spp
+    n = gs.W * gs.H
+    want, cnt = S.render_task(gs.cam, p, gs.W, gs.H)
+    for buf in (np.empty((n, 4), np.float32), np.empty((n, 4), np.float32), np.empty(n * 4 + 1, np.float32)[1:].reshape(n, 4)):
+        for _ in range(2):
+            buf[:] = -1.0
+            got, cnt2 = S.render_task(gs.cam, p, gs.W, gs.H, flags=api.RT_OUT_MEAN | api.RT_FLAG_PIN_HOST, out=buf)
+            assert got is buf and np.array_equal(buf.view(np.uint32), want.view(np.uint32)) and int(cnt2["ray_count"]) == int(cnt["ray_count"])
+    comm = api.Comm.create(1, 0, None, 0)
+    out = np.empty((gs.H, gs.W, 4), np.float32)
+    frame, _, _, _ = api.render_combined(S, comm, gs.cam, p, gs.W, gs.H, partition="tiles", tile=8, flags=api.RT_FLAG_PIN_HOST, want_frame=True, out=out)
+    assert frame is out and np.array_equal(out.reshape(-1, 4).view(np.uint32), want.view(np.uint32))
+    comm.close(); S.close()
