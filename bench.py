@@ -365,13 +365,18 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
 
     # ---- untimed: N > 1 parity of the combined frame against a single-GPU render of the same frame on rank 0 ----
     combine_parity = None
+    combine_max_rel_diff = 0.0
     if world > 1 and parity_check:
         out, _, _, cnt = api.render_combined(S, ctx.comm, cam_h[0], par_h[0], W, H, partition=partition, tile=TILE, flags=base_flags & ~api.RT_FLAG_TIME_KERNELS,
                                              root=0, want_frame=True)
         if rank == 0:
             single, cnt1 = S.render(cam_h[0], par_h[0], W, H, flags=api.RT_OUT_MEAN | (api.RT_FLAG_ADAPTIVE if adaptive else 0))
             if partition == "samples":
-                combine_parity = bool(np.allclose(out, single, rtol=2e-6, atol=1e-7)) and int(cnt["ray_count"]) == int(cnt1["ray_count"])
+                # a different summation tree (N partial sums of spp / N samples instead of one running sum of spp): float32 rounding differs by
+                # ~sqrt(spp) * 2^-24 relative -- observed 2.7e-5 at 4096 spp, bound 1e-6 * sqrt(spp); the ray counts must be equal
+                rel = np.abs(out - single) / np.maximum(np.abs(single), 1e-6)
+                combine_max_rel_diff = float(rel.max())
+                combine_parity = combine_max_rel_diff <= max(2e-6, 1e-6 * math.sqrt(float(params["min_samples"]))) and int(cnt["ray_count"]) == int(cnt1["ray_count"])
             else:
                 combine_parity = bool(np.array_equal(out.view(np.uint32), single.view(np.uint32))) and int(cnt["ray_count"]) == int(cnt1["ray_count"])
         sync_all()
@@ -436,6 +441,7 @@ def measure_workload(ctx, key: str, steps: int, warmup: int, partition: str, wit
     }
     if world > 1:
         out["combine_parity"] = combine_parity
+        out["combine_max_rel_diff"] = combine_max_rel_diff
         out["per_step_ms"] = {"render_gpu_max_over_ranks": max_gpu_ms / steps, "k_trace_wave_max": max_trace_ms / steps, "k_logic_max": max_logic_ms / steps,
                               "reduce_and_resolve_max": max_combine_ms / steps,
                               "note": "render = CUDA-event time of the rank's wave loop; the wave tails (launch + drain of ~25-30 waves x 2 kernels) do not shrink with the tile count"}
@@ -482,7 +488,7 @@ def run_ours(args, rank, world, local_rank):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
         for k in ("config", "clocks", "e2e", "gpu_launches", "roofline"):
             line[k] = head[k]
-        for k in ("combine_parity", "per_step_ms"):
+        for k in ("combine_parity", "combine_max_rel_diff", "per_step_ms"):
             if k in head:
                 line[k] = head[k]
         if cpu is not None:
