@@ -12,7 +12,6 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
-#include <condition_variable>
 #include <mutex>
 #include <thread>
 
@@ -446,7 +445,6 @@ extern "C" int rt_render_combined(rt_scene *scene, rt_comm *comm, const rt_camer
     memset(&cnt, 0, sizeof(cnt));
     rc = render_share(scene, comm, cam, params, width, height, partition, tile, flags, frame, &cnt);
     if (rc) return rc;
-    const rt_stats render_stats = scene->stats;
 
     CK(cudaEventRecord(comm->e0, st));
     if (comm->n > 1) {
@@ -478,7 +476,6 @@ extern "C" int rt_render_combined(rt_scene *scene, rt_comm *comm, const rt_camer
     }
     CK(cudaStreamSynchronize(st));
     { float ms = 0; CK(cudaEventElapsedTime(&ms, comm->e0, comm->e1)); comm->stats[0] = ms; }
-    (void)render_stats;
     if (out_counters) *out_counters = cnt;
     return RT_OK;
 }

@@ -251,7 +251,6 @@ static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint3
     if (L) CK(cudaMemsetAsync(p.counts + 2, 0, 4 * L, st));
 
     uint32_t bound = n_first;                           // upper bound of the closest-hit queue of the wave being issued
-    uint32_t in_closest[RT_COUNT_RING] = {0};           // what the host knew when it issued wave w (for the statistics)
     auto issue = [&](uint32_t w) -> int {
         const int cur = (int)(w & 1u);
         { int rc_ = wave_event(sc, timed); if (rc_) return rc_; }
@@ -289,7 +288,6 @@ static int run_waves(rt_scene *sc, const DevParams &prm, uint32_t n_first, uint3
         bound = c_out;                                  // queue sizes never grow: every live path emits at most one ray per wave
         if (c_out == 0 && sh_out == 0) break;           // the wave already in flight finds empty queues and does nothing
     }
-    (void)in_closest;
     if (timed) sc->wave_log.push_back(std::make_pair((uint64_t)0, (uint64_t)0));      // the run-ahead wave that found empty queues
     if (L > 1) {
         k_fold_light_acc<<<cdiv(n_first, 256), 256, 0, st>>>(p.paths.acc, p.acc_extra, n_first, p.shadow.capacity, L - 1);
