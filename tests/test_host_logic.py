@@ -113,3 +113,37 @@ def test_obj_export_is_what_the_reference_parses():
     bump_ref = rs.textures[int(rs.materials[2]["bump_texture"])]
     # numpy powf vs glibc powf may disagree by one code value at truncation boundaries
     assert np.abs(bump_ref.texels.astype(int) - sd.textures[1].texels.astype(int)).max() <= 1
+
+
+def test_bench_roofline_arithmetic_and_inputs():
+    """bench.py's roofline numerator is SURVEY 8(d)'s algorithmic bytes per ray; its workloads are BASELINE's configurations; the
+    committed traffic file it cites exists and names the dominant kernel."""
+    import importlib.util
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    assert bench.b_ray(63490) == 776 and bench.b_ray(1048352) == 904 and bench.b_ray(9999392) == 1032
+    assert bench.DEFAULT_WORKLOAD == "config3" and bench.WORKLOADS["config3"][:3] == (1920, 1080, 128)
+    assert bench.WORKLOADS["config4"][:3] == (3840, 2160, 256) and bench.WORKLOADS["config2"][:3] == (1920, 1080, 64)
+    traffic, src = bench.measured_traffic("config3", "k_trace_wave")
+    assert src == "profiles/r2_traffic_config3.json" and 1e8 < traffic < 1e9
+    assert bench.measured_traffic("config4", "k_trace_wave") == (None, None)
+    sd = bench.make_scene("config2")
+    cam, params = bench.make_camera_params("config2", sd)
+    assert int(params["min_samples"]) == int(params["max_samples"]) == 64 and sd.n_triangles == 63490
+    cam1, p1 = bench.make_camera_params("config1", scenes.sponza_standin_scene(detail=0.15))
+    assert (int(p1["min_samples"]), int(p1["max_samples"])) == (10, 50)                 # main.cpp:308-309
+    assert np.allclose(cam1["position"], (475.0, 250.0, 0.0))                           # main.cpp:426-431
+
+
+def test_sponza_standin_is_a_valid_one_sided_obj_scene():
+    sd = scenes.sponza_standin_scene()               # full detail: coarser tessellations facet the fluted columns against their radial normals
+    sd.validate()
+    assert 250_000 <= sd.n_triangles <= 320_000
+    assert sd.n_groups >= 200 and sd.tangents is not None
+    a = sd.positions[sd.idx_positions[0::3]]; b = sd.positions[sd.idx_positions[1::3]]; c = sd.positions[sd.idx_positions[2::3]]
+    n = np.cross(b - a, c - a)
+    assert np.all(np.linalg.norm(n, axis=1) > 0)
+    assert np.all(np.einsum("ij,ij->i", n, sd.normals[sd.idx_normals[0::3]]) > 0)       # winding agrees with the shading normals
+    kinds = {k for m in sd.materials for k in ("diffuse_texture", "bump_texture", "alpha_texture") if m[k] >= 0}
+    assert kinds == {"diffuse_texture", "bump_texture", "alpha_texture"} and (sd.materials["alpha"] < 1).any()
