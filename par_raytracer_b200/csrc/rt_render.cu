@@ -202,7 +202,7 @@ static uint32_t env_knob(const char *name, uint32_t dflt) {
 }
 static void set_fetch_knobs(WaveQueues &w) {
     uint32_t a = 0, b = 0, c = 0, d = 0;      // read per launch (microseconds): lets one process sweep the knobs
-    { a = env_knob("RT_B200_FETCH_MIN", RT_FETCH_MIN); b = env_knob("RT_B200_FETCH_PRIMARY", RT_FETCH_MIN); c = env_knob("RT_B200_FETCH_SHADOW", RT_FETCH_MIN);
+    { a = env_knob("RT_B200_FETCH_MIN", RT_FETCH_MIN); b = env_knob("RT_B200_FETCH_PRIMARY", RT_FETCH_PRIMARY); c = env_knob("RT_B200_FETCH_SHADOW", RT_FETCH_MIN);
               d = env_knob("RT_B200_LEAF_WAIT", RT_LEAF_WAIT); }
     w.fetch_min = a; w.fetch_min_primary = b; w.fetch_min_shadow = c; w.leaf_wait = d;
 }

@@ -173,6 +173,9 @@ RT_DEVICE bool qbox_child(uint32_t wx, uint32_t wy, uint32_t wz, const QRay &Q, 
 #ifndef RT_FETCH_MIN
 #define RT_FETCH_MIN 16
 #endif
+#ifndef RT_FETCH_PRIMARY
+#define RT_FETCH_PRIMARY 24         // same threshold while the warp still draws primary rays of wave 0: coherent rays finish together, so waiting for more idle
+#endif                              // lanes costs little and saves refills (measured 8 / 16 / 24 / 32 on config 3: 166.6 / 163.2 / 160.9 / 161.8 ms per frame; config 4: 16 / 24 / 28: 1,557 / 1,524 / 1,518)
 #ifndef RT_LEAF_WAIT
 #define RT_LEAF_WAIT 12
 #endif
