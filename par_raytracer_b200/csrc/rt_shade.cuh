@@ -151,6 +151,9 @@ RT_DEVICE float phong_pow(float x, float e) { return (x == 0.0f && e > 0.0f) ? 0
 #ifndef RT_LOGIC_MIN_BLOCKS
 #define RT_LOGIC_MIN_BLOCKS 6
 #endif
+#ifndef RT_FRAME_LAST_POP
+#define RT_FRAME_LAST_POP 1      // 1: a recursion frame is popped when its last child is taken and holds only the words later children read (0: every frame is pushed whole and re-read once exhausted)
+#endif
 #ifndef RT_LOGIC_CHUNK
 #define RT_LOGIC_CHUNK 256       // queue entries a block sorts by material and deals to its 128 threads at a time (multiple of 128, <= 65536; measured 256 / 512 / 1024 / 2048: profiles/README.md)
 #endif
@@ -315,21 +318,30 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
                 acc = acc + Ta * (ambient * 0.1f);                            // raytracer.cpp:543
                 shade_hit = true;
                 if (iters > 0) {
-                    // children exist: push this node's recursion frame
+                    // Children exist. The first one (a diffuse sample, if there are any) is generated from registers further down; the node's
+                    // recursion frame is pushed only if more children follow, and only with the words those children read: F[2] / F[4] (V,
+                    // specular weight) for specular children and the translucent continuation, F[3] (diffuse weight) for diffuse children
+                    // after the first, F[5] for the continuation. Reference defaults (1 + 1 samples, opaque): 64 bytes, read once.
+                    const uint32_t rs = prm.reflection_samples, ss = prm.spec_samples;
                     f3 Td = (Ta * kd) * w_diffuse;                           // raytracer.cpp:544
                     f3 Ts = Ta * ks;                                         // raytracer.cpp:545
                     f3 Tc = T * (1.0f - alpha);
-                    fresh_frame = prm.reflection_samples > 0;
-                    uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u) | (fresh_frame ? (1u << 8) : 0u);   // next child index in bits 8..30
-                    float4 *F = P.frames + (size_t)(sp * RT_FRAME_F4) * cap + slot;
-                    F[0 * (size_t)cap] = mk4u(hit_p, meta);
-                    F[1 * (size_t)cap] = mk4u(N, (uint32_t)mat_id);
-                    F[2 * (size_t)cap] = mk4(V, spec_int);
-                    F[3 * (size_t)cap] = mk4(Td, Tc.x);
-                    F[4 * (size_t)cap] = mk4(Ts, Tc.y);
-                    if (translucent) F[5 * (size_t)cap] = mk4(position + (V * prm.ray_bias) * 2.0f, Tc.z);   // raytracer.cpp:549
-                    sp++;
+                    fresh_frame = rs > 0;
                     f_Td = Td;
+                    const bool lean = RT_FRAME_LAST_POP != 0;
+                    if (!lean || rs + ss + (translucent ? 1u : 0u) > (fresh_frame ? 1u : 0u)) {
+                        uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u) | (fresh_frame ? (1u << 8) : 0u);   // next child index in bits 8..30
+                        float4 *F = P.frames + (size_t)(sp * RT_FRAME_F4) * cap + slot;
+                        F[0 * (size_t)cap] = mk4u(hit_p, meta);
+                        F[1 * (size_t)cap] = mk4u(N, (uint32_t)mat_id);
+                        if (!lean || ss > 0 || translucent) {
+                            F[2 * (size_t)cap] = mk4(V, spec_int);
+                            F[4 * (size_t)cap] = mk4(Ts, Tc.y);
+                        }
+                        if (!lean || rs > 1 || translucent) F[3 * (size_t)cap] = mk4(Td, Tc.x);
+                        if (translucent) F[5 * (size_t)cap] = mk4(position + (V * prm.ray_bias) * 2.0f, Tc.z);   // raytracer.cpp:549
+                        sp++;
+                    }
                 }
                 // iters == 0: the translucent continuation has iters - 1 < 0 and returns black (raytracer.cpp:416)
             }
@@ -387,8 +399,13 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             int f_iters = (int)(meta & 0xFFu);
             bool has_cont = (meta & 0x80000000u) != 0;
             uint32_t rs = prm.reflection_samples, ss = prm.spec_samples;
-            if (child >= rs + ss + (has_cont ? 1u : 0u)) { sp--; continue; }
-            F[0].w = __uint_as_float((meta & 0x800000FFu) | ((child + 1u) << 8));
+            const uint32_t n_children = rs + ss + (has_cont ? 1u : 0u);
+            if (child >= n_children) { sp--; continue; }                      // RT_FRAME_LAST_POP: guard only, a frame leaves the stack with its last child
+            // The LAST child pops the frame as it is taken (its words are read below, nothing overwrites them before): a path that comes
+            // back from that child finds the grandparent on top and never re-reads an exhausted frame -- one dependent load less per
+            // return, no child-index store for the frames that have one child left (all of them with the reference's 1 + 1 samples).
+            if (RT_FRAME_LAST_POP && child + 1u >= n_children) sp--;
+            else F[0].w = __uint_as_float((meta & 0x800000FFu) | ((child + 1u) << 8));
             if (rng.n >= 14u && rng.seed == 0) rng.seed = P.rng_seed[slot];
             f3 fp = mk3(f0);
             float4 f1 = F[1 * (size_t)cap];
