@@ -83,9 +83,14 @@ static int ensure_pool(rt_scene *sc, uint32_t capacity, uint32_t depth) {
     capacity = std::max(capacity, p.capacity); depth = std::max(depth, p.depth);
     p.capacity = p.depth = 0;
     size_t c = capacity;
-    CK(p.mem.alloc(&p.paths.rng_cx, c)); CK(p.mem.alloc(&p.paths.rng_seed, c));
-    CK(p.mem.alloc(&p.paths.acc, c)); CK(p.mem.alloc(&p.paths.node_T, c));
+#if RT_POOL_AOS
+    CK(p.mem.alloc(&p.paths.node_T, 2 * c)); p.paths.rng_cx = nullptr;          // one 32-byte record per slot: throughput + generator state (rt_types.cuh)
+#else
+    CK(p.mem.alloc(&p.paths.node_T, c)); CK(p.mem.alloc(&p.paths.rng_cx, c));
+#endif
+    CK(p.mem.alloc(&p.paths.rng_seed, c)); CK(p.mem.alloc(&p.paths.acc, c));
     CK(p.mem.alloc(&p.paths.frames, c * RT_FRAME_F4 * depth));
+    p.paths.depth = depth;
     CK(p.mem.alloc(&p.ray_cnt, c));
     p.paths.ray_cnt = nullptr;           // switched on only by the adaptive loop
     p.paths.capacity = capacity;

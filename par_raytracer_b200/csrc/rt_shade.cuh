@@ -24,7 +24,6 @@
 #include "rt_trace.cuh"
 #include "rt_types.cuh"
 
-#define RT_FRAME_F4 6            // float4 words per recursion frame
 
 
 RT_DEVICE uint32_t pack_state(int iters, uint32_t sp, uint32_t draws) { return (uint32_t)iters | (sp << 8) | (draws << 16); }
@@ -57,9 +56,9 @@ __global__ void k_raygen(PrimaryGen g, DevParams prm, PathPool P, RayQueue q, ui
     q.o[s] = mk4(org, 0.0f);
     q.d[s] = mk4u(dir, s);
     P.rng_seed[s] = r.seed;
-    P.rng_cx[s] = rng_pack(r);
+    *path_rng(P, s) = rng_pack(r);
     P.acc[s] = make_float4(0, 0, 0, 0);
-    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
+    *path_T(P, s) = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
     if (s == 0) *n_rays_out = g.n_slots;
 }
 
@@ -74,9 +73,9 @@ __global__ void k_paths_from_rays(DevParams prm, PathPool P, RayQueue q, uint32_
     PathRng r;
     rng_seed(r, seeds[s]);
     P.rng_seed[s] = r.seed;
-    P.rng_cx[s] = rng_pack(r);
+    *path_rng(P, s) = rng_pack(r);
     P.acc[s] = make_float4(0, 0, 0, 0);
-    P.node_T[s] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
+    *path_T(P, s) = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pack_state((int)prm.bounce_depth, 0, r.n)));
     if (s == 0) *n_rays_out = n;
 }
 
@@ -160,7 +159,6 @@ RT_DEVICE float phong_pow(float x, float e) { return (x == 0.0f && e > 0.0f) ? 0
 __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, DevParams prm, PathPool P, RayQueue qin, const HitRec *hits, const uint32_t *n_in_ptr,
                                               uint32_t n_in_max, RayQueue qout, uint32_t *n_out, ShadowQueue sh, PrimaryGen G) {
     const uint32_t n_in = G.enabled ? G.n_slots : min(*n_in_ptr, n_in_max);
-    const uint32_t cap = P.capacity;
     const int bd = (int)prm.bounce_depth;
     // Persistent blocks, block-uniform trip counts (every lane of a warp reaches the warp-aggregated pushes together). A block takes
     // RT_LOGIC_CHUNK consecutive queue entries at a time and deals them to its threads SORTED by (miss | material of the hit triangle):
@@ -244,8 +242,8 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             // every independent load of the path's state is issued before the first use
             float4 o4 = qin.o[i], d4 = qin.d[i];
             slot = __float_as_uint(d4.w);
-            float4 t4 = P.node_T[slot];
-            uint4 cx = P.rng_cx[slot];
+            float4 t4 = *path_T(P, slot);
+            uint4 cx = *path_rng(P, slot);
             float4 a4 = P.acc[slot];
             uint32_t st = __float_as_uint(t4.w);
             T = mk3(t4); iters = (int)(st & 0xFFu); sp = (st >> 8) & 0xFFu;
@@ -331,15 +329,14 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
                     const bool lean = RT_FRAME_LAST_POP != 0;
                     if (!lean || rs + ss + (translucent ? 1u : 0u) > (fresh_frame ? 1u : 0u)) {
                         uint32_t meta = (uint32_t)iters | (translucent ? 0x80000000u : 0u) | (fresh_frame ? (1u << 8) : 0u);   // next child index in bits 8..30
-                        float4 *F = P.frames + (size_t)(sp * RT_FRAME_F4) * cap + slot;
-                        F[0 * (size_t)cap] = mk4u(hit_p, meta);
-                        F[1 * (size_t)cap] = mk4u(N, (uint32_t)mat_id);
+                        *frame_word(P, slot, sp, 0) = mk4u(hit_p, meta);
+                        *frame_word(P, slot, sp, 1) = mk4u(N, (uint32_t)mat_id);
                         if (!lean || ss > 0 || translucent) {
-                            F[2 * (size_t)cap] = mk4(V, spec_int);
-                            F[4 * (size_t)cap] = mk4(Ts, Tc.y);
+                            *frame_word(P, slot, sp, 2) = mk4(V, spec_int);
+                            *frame_word(P, slot, sp, 4) = mk4(Ts, Tc.y);
                         }
-                        if (!lean || rs > 1 || translucent) F[3 * (size_t)cap] = mk4(Td, Tc.x);
-                        if (translucent) F[5 * (size_t)cap] = mk4(position + (V * prm.ray_bias) * 2.0f, Tc.z);   // raytracer.cpp:549
+                        if (!lean || rs > 1 || translucent) *frame_word(P, slot, sp, 3) = mk4(Td, Tc.x);
+                        if (translucent) *frame_word(P, slot, sp, 5) = mk4(position + (V * prm.ray_bias) * 2.0f, Tc.z);   // raytracer.cpp:549
                         sp++;
                     }
                 }
@@ -392,7 +389,8 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             if (!(rng_float01(rng) < 0.5f)) { emit = true; e_org = hit_p; e_dir = c_dir; e_T = c_T; e_iters = iters - 1; }
         }
         while (!emit && sp > 0) {
-            float4 *F = P.frames + (size_t)((sp - 1) * RT_FRAME_F4) * cap + slot;
+            const uint32_t lvl = sp - 1;
+            float4 *F = frame_word(P, slot, lvl, 0);
             float4 f0 = F[0];
             uint32_t meta = __float_as_uint(f0.w);
             uint32_t child = (meta >> 8) & 0x7FFFFFu;
@@ -408,21 +406,21 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             else F[0].w = __uint_as_float((meta & 0x800000FFu) | ((child + 1u) << 8));
             if (rng.n >= 14u && rng.seed == 0) rng.seed = P.rng_seed[slot];
             f3 fp = mk3(f0);
-            float4 f1 = F[1 * (size_t)cap];
+            float4 f1 = *frame_word(P, slot, lvl, 1);
             f3 fn = mk3(f1);
             f3 c_dir, c_T, c_org = fp;
             if (child < rs) {                                                // raytracer.cpp:516-526
                 uint32_t series_i = (uint32_t)(rng_next(rng) % 1024ull);
                 c_dir = to_world(fn, mk3(__ldg(S.hamm_dir + series_i)));
-                float4 f3v = F[3 * (size_t)cap];
+                float4 f3v = *frame_word(P, slot, lvl, 3);
                 c_T = mk3(f3v) * max0(dot3(fn, c_dir));
             } else if (child < rs + ss) {                                    // raytracer.cpp:528-535
                 uint32_t mat_id = __float_as_uint(f1.w);
                 c_dir = to_world(fn, mk3(__ldg(S.spec_dir + (size_t)mat_id * ss + (child - rs))));
-                float4 f2 = F[2 * (size_t)cap], f4 = F[4 * (size_t)cap];
+                float4 f2 = *frame_word(P, slot, lvl, 2), f4 = *frame_word(P, slot, lvl, 4);
                 c_T = mk3(f4) * max0(dot3(c_dir, neg3(mk3(f2))));
             } else {                                                         // raytracer.cpp:547-551
-                float4 f2 = F[2 * (size_t)cap], f3v = F[3 * (size_t)cap], f4 = F[4 * (size_t)cap], f5 = F[5 * (size_t)cap];
+                float4 f2 = *frame_word(P, slot, lvl, 2), f3v = *frame_word(P, slot, lvl, 3), f4 = *frame_word(P, slot, lvl, 4), f5 = *frame_word(P, slot, lvl, 5);
                 c_dir = mk3(f2); c_org = mk3(f5); c_T = mk3(f3v.w, f4.w, f5.w);
             }
             // child node entry (raytracer.cpp:416-420): iters - 1 >= 0 here, and never the root level
@@ -440,8 +438,8 @@ __global__ void __launch_bounds__(128, RT_LOGIC_MIN_BLOCKS) k_logic(DevScene S, 
             else if (add) P.ray_cnt[slot] += add;
         }
         if (emit) {                                    // a finished path only leaves its radiance behind
-            P.rng_cx[slot] = rng_pack(rng);
-            P.node_T[slot] = mk4u(e_T, pack_state(e_iters, sp, rng.n));
+            *path_rng(P, slot) = rng_pack(rng);
+            *path_T(P, slot) = mk4u(e_T, pack_state(e_iters, sp, rng.n));
             if (G.enabled) P.rng_seed[slot] = rng.seed;
         }
     }
