@@ -503,7 +503,18 @@ def run_ours(args, rank, world, local_rank):
     return 0
 
 
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout. Native libraries write there too (NCCL prints "NCCL version ..." on the first communicator when
+    NCCL_DEBUG is set, as it is on the GPU boxes), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the
+    original descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -525,4 +536,6 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush()
+    sys.exit(rc)
