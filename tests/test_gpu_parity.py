@@ -220,13 +220,14 @@ def test_child_bound_variants_far_from_origin(bounds, monkeypatch):
 
 
 def test_param_variants_against_oracle():
-    """bounce depth 0 / 1 / 3, several reflection and specular samples, > 15 draws per sample (ring wrap)."""
+    """bounce depth 0 / 1 / 3, several reflection and specular samples, > 15 draws per sample (ring wrap); one-child and no-child nodes
+    (1 + 0, 0 + 1, 0 + 0 samples: the recursion frame is not pushed at all unless the hit is translucent)."""
     sd = scenes.spheres_plane_scene(grid=2, nu=16, nv=8, textured=True)
     S = api.Scene(sd); O = oracle.OracleScene(sd)
     W, H = 64, 48
     h = sd.camera_hint
     cam = types.make_camera(h["fov"], W, H, h["position"], h["facing"])
-    for bd, rs, ss in ((0, 1, 1), (1, 2, 0), (1, 0, 3), (3, 2, 2), (2, 3, 1)):
+    for bd, rs, ss in ((0, 1, 1), (1, 2, 0), (1, 0, 3), (3, 2, 2), (2, 3, 1), (2, 1, 0), (2, 0, 1), (2, 0, 0), (3, 1, 0), (1, 1, 1)):
         p = types.default_params(spp=2)
         p["bounce_depth"] = bd; p["reflection_samples"] = rs; p["spec_samples"] = ss
         img, cnt = S.render(cam, p, W, H)
