@@ -38,7 +38,7 @@ static NcclApi *nccl_api() {
         const char *names[] = {getenv("RT_B200_NCCL"), "libnccl.so.2", "libnccl.so"};
         void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);      // the copy the host process already uses (e.g. torch's)
         for (int k = 0; !h && k < 3; ++k) if (names[k]) h = dlopen(names[k], RTLD_NOW | RTLD_GLOBAL);
-        if (!h) { api.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return; }
+        if (!h) { const char *de = dlerror(); api.why = std::string("libnccl.so.2 not found: ") + (de ? de : ""); return; }     // dlerror() clears itself: call it once
 #define RT_SYM(field, name) do { *(void **)(&api.field) = dlsym(h, name); if (!api.field) { api.why = "symbol " name " missing in libnccl"; return; } } while (0)
         RT_SYM(GetUniqueId, "ncclGetUniqueId"); RT_SYM(CommInitRank, "ncclCommInitRank"); RT_SYM(CommInitAll, "ncclCommInitAll");
         RT_SYM(CommDestroy, "ncclCommDestroy"); RT_SYM(Reduce, "ncclReduce"); RT_SYM(GetErrorString, "ncclGetErrorString");
