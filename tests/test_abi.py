@@ -140,3 +140,24 @@ def test_quantisation_grid_placement(lib):
     for lo, hi in [((0, 0, 0), (np.inf, 1, 1)), ((np.nan, 0, 0), (1, 1, 1)), ((-np.inf, 0, 0), (np.inf, 1, 1))]:
         assert grid(lo, hi)[2] == 0
     assert lib.rt_quant_grid(None, None, None, None, None) != 0
+
+
+def test_header_is_plain_c_and_cxx11(tmp_path):
+    """The boundary is a C ABI: include/rt_b200.h must compile on its own as C99 and as C++11 (the reference's dialect, build.sh:6),
+    with the struct sizes the reference's own headers have."""
+    import shutil
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    body = ('#include "rt_b200.h"\n'
+            'typedef char camera_is_64[sizeof(rt_camera) == 64 ? 1 : -1];\n'
+            'typedef char ray_is_24[sizeof(rt_ray) == 24 ? 1 : -1];\n'
+            'typedef char bsphere_is_24[sizeof(rt_bsphere) == 24 ? 1 : -1];\n'
+            'typedef char hit_is_52[sizeof(rt_hit) == 52 ? 1 : -1];\n'
+            'int main(void) { int (*f)(void) = rt_abi_version; (void)f; return 0; }\n')
+    for cc, flags, name in (("gcc", ["-std=c99", "-pedantic-errors"], "t.c"), ("g++", ["-std=c++11"], "t.cpp")):
+        if not shutil.which(cc):
+            pytest.skip(f"{cc} not installed")
+        src = tmp_path / name
+        src.write_text(body)
+        r = subprocess.run([cc] + flags + ["-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
